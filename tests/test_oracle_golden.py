@@ -1,0 +1,79 @@
+"""The oracle restatement against outputs of the reference itself (tests/golden, minted by
+oracle/make_golden.py from /root/reference/LINAS-engine).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, case_inputs, load_golden
+from oracle import linas
+
+CASES = ["tiny_ragged", "small_cpv20", "c1_1k"]
+
+
+def test_apscorer_known_answers():
+    with open(os.path.join(GOLDEN, "apscorer.json")) as f:
+        cases = json.load(f)
+    assert len(cases) >= 20
+    for c in cases:
+        k = int(c["scorer"].split("@")[1]) if "@" in c["scorer"] else 0
+        assert linas.ap_score(c["labels"], k) == c["score"], c
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("tag,cast", [("f32", np.float32), ("f64", np.float64)])
+def test_full_path_matches_reference(manifest, name, tag, cast):
+    V, Q, vid_ids, cap_ids, _ = case_inputs(manifest, name)
+    g = load_golden(name)
+    errors = linas.cal_error(V.astype(cast), Q.astype(cast))
+    assert errors.dtype == cast
+    np.testing.assert_array_equal(errors[:8, :8], g["errors_head_" + tag])
+    assert errors.astype(np.float64).sum() == g["errors_sum_" + tag]
+    v2t_gt, t2v_gt = linas.get_gt(vid_ids, cap_ids)
+    np.testing.assert_array_equal(linas.gt_ranks(errors, t2v_gt), g["t2v_ranks_" + tag])
+    np.testing.assert_array_equal(linas.gt_ranks(errors.T, v2t_gt), g["v2t_ranks_" + tag])
+    perf = np.array(linas.cal_perf(errors, v2t_gt, t2v_gt), dtype=np.float64)
+    np.testing.assert_array_equal(perf, g["perf_" + tag])       # bit-identical floats
+    top10 = np.stack([linas.topk_ids(errors[i], 10) for i in range(min(64, len(errors)))])
+    np.testing.assert_array_equal(top10, g["top10_" + tag])
+
+
+def test_containers_and_elementwise(manifest):
+    V, Q, vid_ids, cap_ids, _ = case_inputs(manifest, "tiny_ragged")
+    rec, g = manifest["tiny_ragged"], load_golden("tiny_ragged")
+    v2t_gt, t2v_gt = linas.get_gt(vid_ids, cap_ids)
+    assert v2t_gt == rec["v2t_gt"]
+    assert {str(k): v for k, v in t2v_gt.items()} == rec["t2v_gt"]
+    assert list(t2v_gt.keys()) == [int(k) for k in rec["t2v_gt"].keys()]      # same insertion order
+    assert any(len(x) == 0 for x in v2t_gt)                                   # ragged: empty rows exist
+    for tag, cast in (("f32", np.float32), ("f64", np.float64)):
+        Vc, Qc = V.astype(cast), Q.astype(cast)
+        np.testing.assert_array_equal(linas.cal_error(Vc, Qc), g["errors_" + tag])
+        np.testing.assert_array_equal(linas.cal_simi(Qc, Vc), g["simi_" + tag])
+        np.testing.assert_array_equal(linas.norm_score(g["errors_" + tag]), g["norm_score_" + tag])
+        np.testing.assert_array_equal(linas.l2norm(Vc), g["l2norm_" + tag])
+
+
+def test_legacy_metrics(manifest):
+    from cross_modal_video_engine_b200 import synth
+    from conftest import input_sha256
+    rec = manifest["legacy"]
+    V, Q, _, _, _ = synth.msrvtt_like(rec["seed"], 40, 5, 48, 2.0)
+    assert input_sha256(V, Q) == rec["input_sha256"]
+    errors = linas.cal_error(V.astype(np.float64), Q.astype(np.float64))
+    assert linas.t2v(errors, 5) == rec["t2v"]
+    assert linas.v2t(errors, 5) == rec["v2t"]
+    assert float(linas.t2v_inv_rank(errors, 5)) == rec["t2v_inv_rank"]
+    assert float(linas.v2t_inv_rank(errors, 5)) == rec["v2t_inv_rank"]
+    assert [float(x) for x in linas.v2t_inv_rank_multi(errors, 5)] == rec["v2t_inv_rank_multi"]
+
+
+def test_multifusion_time_process_golden(manifest):
+    import torch
+    from cross_modal_video_engine_b200 import synth
+    from oracle import multifusion
+    if "unavailable" in manifest["mf_time_process"]:
+        pytest.skip("reference combiner was not importable when goldens were minted")
+    x = torch.from_numpy(synth.gaussian(31, 37 * 8, 640).reshape(37, 8, 640))
+    np.testing.assert_array_equal(multifusion.time_process(x).numpy(), load_golden("mf_time_process")["pooled"])

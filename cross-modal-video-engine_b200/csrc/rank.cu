@@ -1,0 +1,284 @@
+// K4: bit-exact rank / metric kernels over a caller-supplied errors matrix, and norm_score.
+//
+// The reference finds the rank of every ground-truth item by fully sorting every row (and every
+// strided column) and searching the permutation in Python (LINAS-engine/util/metrics.py:61-102,
+// 124-157; 78 s of the 122 s at the MSR-VTT full-test shape).  A rank is just a count:
+//   rank(g) = 1 + #{m : x[m] < x[g]} + #{m < g : x[m] == x[g]}
+// (the position of g in a stable ascending argsort), so one streaming pass over the matrix gives
+// all ranks exactly; R@K, MedR (histogram), MeanR (integer sum) and AP (double-precision sums in
+// rank order, basic/metric.py:31-46) follow without any floating-point freedom.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace xmve {
+namespace {
+
+constexpr int GT_GROUP = 8;      // ground-truth items ranked per pass over the data
+
+// axis 0: query = row i.  One block per (row, group of GT_GROUP ground-truth entries).
+template <typename T>
+__global__ void __launch_bounds__(256)
+gt_ranks_rows_kernel(const T* __restrict__ x, int64_t n_col, int64_t ld, const int64_t* __restrict__ gt_off,
+                     const int32_t* __restrict__ gt_ids, int32_t* __restrict__ ranks) {
+  const int64_t q = blockIdx.x;
+  const int64_t e0 = gt_off[q] + static_cast<int64_t>(blockIdx.y) * GT_GROUP;
+  const int64_t e1 = min(gt_off[q + 1], e0 + GT_GROUP);
+  if (e0 >= e1) return;
+  const int ng = static_cast<int>(e1 - e0);
+  const T* __restrict__ row = x + q * ld;
+  __shared__ int s_cnt[GT_GROUP];
+  T gv[GT_GROUP];
+  int gi[GT_GROUP], cnt[GT_GROUP];
+#pragma unroll
+  for (int g = 0; g < GT_GROUP; ++g) {
+    gi[g] = g < ng ? gt_ids[e0 + g] : 0;
+    gv[g] = row[gi[g]];
+    cnt[g] = 0;
+  }
+  if (threadIdx.x < GT_GROUP) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (int64_t m = threadIdx.x; m < n_col; m += blockDim.x) {
+    const T v = row[m];
+#pragma unroll
+    for (int g = 0; g < GT_GROUP; ++g) cnt[g] += (v < gv[g] || (v == gv[g] && m < gi[g])) ? 1 : 0;
+  }
+#pragma unroll
+  for (int g = 0; g < GT_GROUP; ++g) {
+    int c = cnt[g];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && g < ng) atomicAdd(&s_cnt[g], c);
+  }
+  __syncthreads();
+  if (threadIdx.x < ng) ranks[e0 + threadIdx.x] = 1 + s_cnt[threadIdx.x];
+}
+
+// axis 1: query = column i, memories = rows.  A block owns 32 adjacent columns (lane <-> column, so
+// every row read is one coalesced line) and a slice of the rows; partial counts are added atomically
+// into ranks[] (zeroed by the host wrapper; slice 0 adds the leading 1).
+template <typename T>
+__global__ void __launch_bounds__(256)
+gt_ranks_cols_kernel(const T* __restrict__ x, int64_t n_row, int64_t n_col, int64_t ld,
+                     const int64_t* __restrict__ gt_off, const int32_t* __restrict__ gt_ids, int max_gt,
+                     int rows_per_slice, int32_t* __restrict__ ranks) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t col = static_cast<int64_t>(blockIdx.x) * 32 + lane;
+  const bool col_ok = col < n_col;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_slice;
+  const int64_t r1 = min(n_row, r0 + rows_per_slice);
+  const int64_t e_lo = col_ok ? gt_off[col] : 0, e_hi = col_ok ? gt_off[col + 1] : 0;
+  for (int base = 0; base < max_gt; base += GT_GROUP) {
+    T gv[GT_GROUP];
+    int gi[GT_GROUP], cnt[GT_GROUP];
+#pragma unroll
+    for (int g = 0; g < GT_GROUP; ++g) {
+      const bool ok = e_lo + base + g < e_hi;
+      gi[g] = ok ? gt_ids[e_lo + base + g] : -1;
+      gv[g] = ok ? x[static_cast<int64_t>(gi[g]) * ld + col] : static_cast<T>(0);
+      cnt[g] = 0;
+    }
+    if (col_ok) {
+      for (int64_t m = r0 + warp; m < r1; m += 8) {
+        const T v = x[m * ld + col];
+#pragma unroll
+        for (int g = 0; g < GT_GROUP; ++g) cnt[g] += (v < gv[g] || (v == gv[g] && m < gi[g])) ? 1 : 0;
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < GT_GROUP; ++g) {
+      if (gi[g] >= 0) {
+        const int add = cnt[g] + ((blockIdx.y == 0 && warp == 0) ? 1 : 0);
+        if (add != 0) atomicAdd(&ranks[e_lo + base + g], add);
+      }
+    }
+  }
+}
+
+// One block per query: sort the query's ranks, reduce to best rank / AP, bump the global tallies.
+__global__ void __launch_bounds__(128)
+rank_metrics_kernel(const int32_t* __restrict__ ranks, const int64_t* __restrict__ gt_off, int64_t n_mem,
+                    int first_only, int ap_k, int32_t* __restrict__ best, double* __restrict__ ap,
+                    unsigned long long* __restrict__ recall_counts, unsigned long long* __restrict__ rank_sum,
+                    int32_t* __restrict__ hist) {
+  extern __shared__ int32_t s_rank[];
+  const int64_t q = blockIdx.x;
+  const int64_t e0 = gt_off[q], e1 = gt_off[q + 1];
+  const int n = static_cast<int>(e1 - e0);
+  int P = 1;
+  while (P < n) P <<= 1;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) s_rank[i] = i < n ? ranks[e0 + i] : 0x7fffffff;
+  __syncthreads();
+  const int first_rank = n > 0 ? s_rank[0] : 0;               // rank of the FIRST ground-truth entry
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < P; t += blockDim.x) {
+        const int o = t ^ stride;
+        if (o > t) {
+          const bool asc = (t & size) == 0;
+          const int a = s_rank[t], b = s_rank[o];
+          if (asc ? (b < a) : (a < b)) { s_rank[t] = b; s_rank[o] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  if (threadIdx.x == 0) {
+    const int64_t length = (ap_k > 0 && ap_k <= n_mem) ? ap_k : n_mem;      // MetricScorer.getLength
+    const int b = n > 0 ? s_rank[0] : static_cast<int>(n_mem + 1);
+    double a = 0.0;
+    if (n > 0) {
+      if (first_only) {
+        if (first_rank <= length) a += 1.0 / static_cast<double>(first_rank);
+        a /= 1.0;
+      } else {
+        for (int j = 0; j < n && s_rank[j] <= length; ++j) a += static_cast<double>(j + 1) / static_cast<double>(s_rank[j]);
+        a /= static_cast<double>(n);
+      }
+    }
+    if (best) best[q] = b;
+    if (ap) ap[q] = a;
+    if (recall_counts) {
+      if (b <= 1) atomicAdd(&recall_counts[0], 1ull);
+      if (b <= 5) atomicAdd(&recall_counts[1], 1ull);
+      if (b <= 10) atomicAdd(&recall_counts[2], 1ull);
+    }
+    if (rank_sum) atomicAdd(rank_sum, static_cast<unsigned long long>(b));
+    if (hist) atomicAdd(&hist[b], 1);
+  }
+}
+
+// ---- norm_score ----------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long dkey(double x) {        // order-preserving key
+  const unsigned long long u = static_cast<unsigned long long>(__double_as_longlong(x));
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_d(unsigned long long k) {
+  return __longlong_as_double(static_cast<long long>((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+
+__global__ void minmax_init_kernel(unsigned long long* keys) {
+  keys[0] = ~0ull;   // running min key
+  keys[1] = 0ull;    // running max key
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+minmax_kernel(const T* __restrict__ x, int64_t n_row, int64_t n_col, int64_t ld, unsigned long long* keys) {
+  double mn = CUDART_INF, mx = -CUDART_INF;
+  const int64_t total = n_row * n_col;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const double s = -static_cast<double>(x[(i / n_col) * ld + (i % n_col)]);   // score = -error
+    mn = fmin(mn, s);
+    mx = fmax(mx, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&keys[0], dkey(mn));
+    atomicMax(&keys[1], dkey(mx));
+  }
+}
+
+// out = -(((-E) - min) / max(-E - min)) in the input's own precision (validate.py:8-11)
+template <typename T>
+__global__ void __launch_bounds__(256)
+norm_apply_kernel(const T* __restrict__ x, int64_t n_row, int64_t n_col, int64_t ld, T* __restrict__ out,
+                  int64_t out_ld, const unsigned long long* __restrict__ keys) {
+  const T mn = static_cast<T>(key_d(keys[0]));
+  const T mx = static_cast<T>(key_d(keys[1])) - mn;            // max(s - min) == max(s) - min (monotone)
+  const int64_t total = n_row * n_col;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / n_col, c = i % n_col;
+    const T s = -x[r * ld + c];
+    out[r * out_ld + c] = -((s - mn) / mx);
+  }
+}
+
+}  // namespace
+}  // namespace xmve
+
+extern "C" int xmve_gt_ranks(const void* errors, int dtype, int64_t n_row, int64_t n_col, int64_t ld, int axis,
+                             const int64_t* gt_off, const int32_t* gt_ids, int64_t n_query, int64_t n_entries,
+                             int32_t max_gt, int32_t* ranks, void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  XMVE_REQUIRE(errors && gt_off && gt_ids && ranks && n_row > 0 && n_col > 0 && ld >= n_col, "gt_ranks: bad arguments");
+  XMVE_REQUIRE(dtype == XMVE_F32 || dtype == XMVE_F64, "gt_ranks: dtype must be f32 or f64");
+  XMVE_REQUIRE(axis == 0 || axis == 1, "gt_ranks: axis must be 0 or 1");
+  XMVE_REQUIRE(n_query == (axis == 0 ? n_row : n_col), "gt_ranks: n_query must match the query axis");
+  XMVE_REQUIRE(n_entries >= 0 && max_gt >= 0, "gt_ranks: negative CSR sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_entries == 0 || max_gt == 0) return XMVE_OK;
+  if (axis == 0) {
+    dim3 grid(static_cast<unsigned>(n_query), static_cast<unsigned>((max_gt + GT_GROUP - 1) / GT_GROUP));
+    if (grid.y > 65535) return fail(XMVE_ERR_LIMIT, "gt_ranks: too many ground-truth entries per query");
+    if (dtype == XMVE_F32)
+      gt_ranks_rows_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(errors), n_col, ld, gt_off, gt_ids, ranks);
+    else
+      gt_ranks_rows_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(errors), n_col, ld, gt_off, gt_ids, ranks);
+  } else {
+    XMVE_CUDA(cudaMemsetAsync(ranks, 0, static_cast<size_t>(n_entries) * sizeof(int32_t), st));
+    const int col_blocks = static_cast<int>((n_col + 31) / 32);
+    int slices = (4 * sm_count() + col_blocks - 1) / col_blocks;
+    if (slices < 1) slices = 1;
+    int rows_per_slice = static_cast<int>((n_row + slices - 1) / slices);
+    rows_per_slice = (rows_per_slice + 7) / 8 * 8;
+    slices = static_cast<int>((n_row + rows_per_slice - 1) / rows_per_slice);
+    dim3 grid(static_cast<unsigned>(col_blocks), static_cast<unsigned>(slices));
+    if (dtype == XMVE_F32)
+      gt_ranks_cols_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(errors), n_row, n_col, ld, gt_off,
+                                                        gt_ids, max_gt, rows_per_slice, ranks);
+    else
+      gt_ranks_cols_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(errors), n_row, n_col, ld, gt_off,
+                                                         gt_ids, max_gt, rows_per_slice, ranks);
+  }
+  return launch_status("gt_ranks kernel");
+}
+
+extern "C" int xmve_rank_metrics(const int32_t* ranks, const int64_t* gt_off, int64_t n_query, int64_t n_mem,
+                                 int first_only, int ap_k, int32_t* best, double* ap, int64_t* recall_counts,
+                                 int64_t* rank_sum, int32_t* hist, void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  XMVE_REQUIRE(ranks && gt_off && n_query >= 0 && n_mem > 0, "rank_metrics: bad arguments");
+  if (n_query == 0) return XMVE_OK;
+  const int smem = 16384 * static_cast<int>(sizeof(int32_t));      // up to 16384 GT entries per query
+  static bool attr_set = false;
+  if (!attr_set) {
+    XMVE_CUDA(cudaFuncSetAttribute(rank_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  rank_metrics_kernel<<<static_cast<unsigned>(n_query), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+      ranks, gt_off, n_mem, first_only, ap_k, best, ap, reinterpret_cast<unsigned long long*>(recall_counts),
+      reinterpret_cast<unsigned long long*>(rank_sum), hist);
+  return launch_status("rank_metrics_kernel");
+}
+
+extern "C" int xmve_norm_score(const void* errors, int dtype, int64_t n_row, int64_t n_col, int64_t ld, void* out,
+                               int64_t out_ld, double* minmax_scratch, void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  XMVE_REQUIRE(errors && out && minmax_scratch && n_row > 0 && n_col > 0 && ld >= n_col && out_ld >= n_col,
+               "norm_score: bad arguments");
+  XMVE_REQUIRE(dtype == XMVE_F32 || dtype == XMVE_F64, "norm_score: dtype must be f32 or f64");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(minmax_scratch);
+  const int grid = 8 * sm_count();
+  minmax_init_kernel<<<1, 1, 0, st>>>(keys);
+  if (dtype == XMVE_F32) {
+    minmax_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(errors), n_row, n_col, ld, keys);
+    norm_apply_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(errors), n_row, n_col, ld,
+                                                   static_cast<float*>(out), out_ld, keys);
+  } else {
+    minmax_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(errors), n_row, n_col, ld, keys);
+    norm_apply_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(errors), n_row, n_col, ld,
+                                                    static_cast<double*>(out), out_ld, keys);
+  }
+  return launch_status("norm_score kernels");
+}

@@ -1,0 +1,167 @@
+// Exact (double precision) scoring: the candidate rescore after the bf16 tensor-core filter pass,
+// and a tiled fp64 score matrix for small problems.
+//
+// The reference's natural dtype on this path is float64: encode_vid / encode_text store fp32 model
+// outputs into np.zeros (float64) arrays (LINAS-engine/evaluation.py:102-105,134,157) and cal_error
+// normalises and multiplies them in double (:19-21).  Both kernels below reproduce that arithmetic
+// (fp32-valued inputs, fp64 products and sums) up to summation order, which is what makes the
+// returned top-k order and the ground-truth ranks identical to the reference's.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace xmve {
+namespace {
+
+constexpr int RS_WARPS = 8;
+constexpr int MAX_SPACES = 8;
+
+struct SpaceDesc {
+  int n_space;
+  int off[MAX_SPACES + 1];
+  double w[MAX_SPACES];
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One block per query row; its warps walk the row's candidate slots.
+__global__ void __launch_bounds__(RS_WARPS * 32)
+rescore_kernel(const float* __restrict__ q_raw, int64_t nq, int64_t q_ld, const double* __restrict__ q_norm,
+               const float* __restrict__ v_raw, int64_t nv, int64_t v_ld, const double* __restrict__ v_norm,
+               const SpaceDesc sp, int norm_mode, const float* __restrict__ cand_score,
+               const int32_t* __restrict__ cand_idx, const int32_t* __restrict__ cand_count, int cap,
+               const float* __restrict__ bound, double* __restrict__ exact) {
+  extern __shared__ __align__(16) float q_s[];
+  const int64_t q = blockIdx.x;
+  const int dtot = sp.off[sp.n_space];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < dtot; i += blockDim.x) q_s[i] = q_raw[q * q_ld + i];
+  __syncthreads();
+  const int n = min(cand_count[q], cap);
+  const float bnd = bound ? bound[q] : -CUDART_INF_F;
+  const bool vec = (v_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(v_raw) & 15u) == 0);
+  for (int c = warp; c < n; c += RS_WARPS) {                   // slots >= n are never read downstream
+    double res = -CUDART_INF;
+    if (cand_score[q * cap + c] >= bnd) {
+      const int64_t v = cand_idx[q * cap + c];
+      const float* __restrict__ vr = v_raw + v * v_ld;
+      res = 0.0;
+      for (int s = 0; s < sp.n_space; ++s) {
+        const int lo = sp.off[s], hi = sp.off[s + 1];
+        double acc = 0.0;
+        if (vec && (lo % 4 == 0) && ((hi - lo) % 4 == 0)) {
+          const float4* v4 = reinterpret_cast<const float4*>(vr + lo);
+          const float4* q4 = reinterpret_cast<const float4*>(q_s + lo);
+          for (int i = lane; i < (hi - lo) / 4; i += 32) {
+            const float4 a = q4[i], b = v4[i];
+            acc += static_cast<double>(a.x) * b.x;
+            acc += static_cast<double>(a.y) * b.y;
+            acc += static_cast<double>(a.z) * b.z;
+            acc += static_cast<double>(a.w) * b.w;
+          }
+        } else {
+          for (int i = lo + lane; i < hi; i += 32) acc += static_cast<double>(q_s[i]) * static_cast<double>(vr[i]);
+        }
+        acc = warp_sum(acc);
+        double nqv = q_norm[static_cast<int64_t>(s) * nq + q], nvv = v_norm[static_cast<int64_t>(s) * nv + v];
+        if (norm_mode == XMVE_NORM_EPS) {
+          nqv = fmax(nqv, 1e-12);
+          nvv = fmax(nvv, 1e-12);
+        }
+        res += sp.w[s] * (acc / (nqv * nvv));
+      }
+    }
+    if (lane == 0) exact[q * cap + c] = res;
+  }
+}
+
+// ---- tiled fp64 score matrix: out = alpha * A * B^T ----------------------------------------------
+constexpr int TM = 64, TN = 64, TK = 16;   // 256 threads, 4 x 4 outputs each
+
+__global__ void __launch_bounds__(256)
+score_f64_kernel(const double* __restrict__ a, int64_t nq, int64_t a_ld, const double* __restrict__ b, int64_t nv,
+                 int64_t b_ld, int k, double alpha, double* __restrict__ out, int64_t out_ld) {
+  __shared__ double as[TK][TM + 1];
+  __shared__ double bs[TK][TN + 1];
+  const int64_t q0 = static_cast<int64_t>(blockIdx.y) * TM, v0 = static_cast<int64_t>(blockIdx.x) * TN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4] = {};
+  for (int k0 = 0; k0 < k; k0 += TK) {
+    for (int e = threadIdx.x; e < TM * TK; e += 256) {
+      const int r = e / TK, c = e % TK;
+      as[c][r] = (q0 + r < nq && k0 + c < k) ? a[(q0 + r) * a_ld + k0 + c] : 0.0;
+      bs[c][r] = (v0 + r < nv && k0 + c < k) ? b[(v0 + r) * b_ld + k0 + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < TK; ++c) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        av[i] = as[c][ty * 4 + i];
+        bv[i] = bs[c][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t q = q0 + ty * 4 + i, v = v0 + tx * 4 + j;
+      if (q < nq && v < nv) out[q * out_ld + v] = alpha * acc[i][j];
+    }
+}
+
+}  // namespace
+}  // namespace xmve
+
+extern "C" int xmve_rescore(const float* q_raw, int64_t nq, int64_t q_ld, const double* q_norm, const float* v_raw,
+                            int64_t nv, int64_t v_ld, const double* v_norm, int n_space, const int32_t* space_off,
+                            const double* weights, int norm_mode, const float* cand_score, const int32_t* cand_idx,
+                            const int32_t* cand_count, int32_t cap, const float* bound, double* exact,
+                            void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  XMVE_REQUIRE(q_raw && q_norm && v_raw && v_norm && space_off && weights && cand_score && cand_idx && cand_count &&
+                   exact, "rescore: null pointer");
+  XMVE_REQUIRE(n_space >= 1 && n_space <= MAX_SPACES, "rescore: n_space must be in [1, %d]", MAX_SPACES);
+  XMVE_REQUIRE(nq >= 0 && nv > 0 && cap > 0, "rescore: bad sizes");
+  SpaceDesc sp;
+  sp.n_space = n_space;
+  for (int s = 0; s <= n_space; ++s) sp.off[s] = space_off[s];      // host arrays (tiny)
+  for (int s = 0; s < n_space; ++s) {
+    sp.w[s] = weights[s];
+    XMVE_REQUIRE(sp.off[s + 1] > sp.off[s], "rescore: space offsets must increase");
+  }
+  const int dtot = sp.off[n_space];
+  XMVE_REQUIRE(sp.off[0] == 0 && dtot <= q_ld && dtot <= v_ld, "rescore: offsets exceed the raw row length");
+  if (dtot > 8192) return fail(XMVE_ERR_LIMIT, "rescore: total raw dim %d > 8192", dtot);
+  if (nq == 0) return XMVE_OK;
+  rescore_kernel<<<static_cast<unsigned>(nq), RS_WARPS * 32, dtot * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      q_raw, nq, q_ld, q_norm, v_raw, nv, v_ld, v_norm, sp, norm_mode, cand_score, cand_idx, cand_count, cap, bound,
+      exact);
+  return launch_status("rescore_kernel");
+}
+
+extern "C" int xmve_score_f64(const double* a, int64_t nq, int64_t a_ld, const double* b, int64_t nv, int64_t b_ld,
+                              int k, double alpha, double* out, int64_t out_ld, void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  XMVE_REQUIRE(a && b && out && nq >= 0 && nv >= 0 && k > 0 && a_ld >= k && b_ld >= k && out_ld >= nv,
+               "score_f64: bad arguments");
+  if (nq == 0 || nv == 0) return XMVE_OK;
+  dim3 grid(static_cast<unsigned>((nv + TN - 1) / TN), static_cast<unsigned>((nq + TM - 1) / TM));
+  if (grid.y > 65535) return fail(XMVE_ERR_LIMIT, "score_f64: more than %d query rows; chunk the call", 65535 * TM);
+  score_f64_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, nq, a_ld, b, nv, b_ld, k, alpha, out,
+                                                                       out_ld);
+  return launch_status("score_f64_kernel");
+}

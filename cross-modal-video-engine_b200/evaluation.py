@@ -1,0 +1,115 @@
+"""Drop-in for the scoring functions of ``LINAS-engine/evaluation.py`` (same names, argument order,
+return conventions), running on hand-written sm_100a kernels through libxmve.
+
+* ``l2norm(X)``                       evaluation.py:10-14
+* ``cal_error(videos, captions)``     evaluation.py:17-36 (cosine branch) -> errors = -cosine, [Nq, Nv]
+* ``cal_error_batch(...)``            evaluation.py:41-72 (cosine branch is identical)
+* ``cal_simi(captions, videos)``      evaluation.py:75-84 (+cosine; NOTE the swapped argument order)
+
+dtype follows the input, like the reference: float64 arrays (what ``encode_vid`` / ``encode_text``
+produce, evaluation.py:102,134) are scored by the exact fp64 kernel; float32 arrays by the tcgen05
+kernel with split-bf16 (x3) operands, |error| ~ 1e-6.  Only ``measure='cosine'`` is on the hot path
+(SURVEY.md section 8a A2); the cdist / jaccard measures are out of scope and raise.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+_BM, _BN = 128, 256
+
+
+def _dev():
+    N.require_device()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _host_in(x):
+    """ndarray / tensor -> (CUDA tensor fp32|fp64 contiguous, was_numpy)."""
+    was_numpy = not torch.is_tensor(x)
+    t = torch.from_numpy(np.ascontiguousarray(x)) if was_numpy else x
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float64)
+    return t.to(_dev(), non_blocking=True).contiguous(), was_numpy
+
+
+def _out(t, was_numpy):
+    return t.cpu().numpy() if was_numpy else t
+
+
+def _dt(t):
+    return N.F64 if t.dtype == torch.float64 else N.F32
+
+
+def l2norm(X):
+    """Row-wise ``X / ||X||`` (no epsilon), dtype preserved; evaluation.py:10-14."""
+    x, was_numpy = _host_in(X)
+    n, d = x.shape
+    out = torch.empty((n, d), dtype=torch.float64, device=x.device)
+    N.call("xmve_normalize_f64", N.ptr(x), _dt(x), n, d, x.stride(0), N.ptr(out), d, N.NORM_PLAIN, N.stream_ptr())
+    return _out(out.to(x.dtype), was_numpy)
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def score_matrix(queries, corpus, alpha, norm_mode=N.NORM_PLAIN):
+    """``alpha * l2norm(queries) @ l2norm(corpus).T`` on the device, dtype of the inputs."""
+    q, _ = _host_in(queries)
+    v, _ = _host_in(corpus)
+    if q.dtype != v.dtype:
+        q, v = q.to(torch.float64), v.to(torch.float64)
+    nq, d = q.shape
+    nv = v.shape[0]
+    assert v.shape[1] == d, "embedding dims differ"
+    st = N.stream_ptr()
+    if nq == 0 or nv == 0:
+        return torch.empty((nq, nv), dtype=q.dtype, device=q.device)
+    if q.dtype == torch.float64:
+        qn = torch.empty((nq, d), dtype=torch.float64, device=q.device)
+        vn = torch.empty((nv, d), dtype=torch.float64, device=q.device)
+        N.call("xmve_normalize_f64", N.ptr(q), N.F64, nq, d, q.stride(0), N.ptr(qn), d, norm_mode, st)
+        N.call("xmve_normalize_f64", N.ptr(v), N.F64, nv, d, v.stride(0), N.ptr(vn), d, norm_mode, st)
+        out = torch.empty((nq, nv), dtype=torch.float64, device=q.device)
+        step = 1 << 21
+        for q0 in range(0, nq, step):
+            q1 = min(nq, q0 + step)
+            N.call("xmve_score_f64", N.ptr(qn[q0:]), q1 - q0, d, N.ptr(vn), nv, d, d, float(alpha),
+                   N.ptr(out[q0:]), nv, st)
+        return out
+    # float32: tensor-core path, split-bf16 operands  A = [hi | hi | lo],  B = [hi | lo | hi]
+    dpad = _round_up(d, 64)
+    a_op = torch.zeros((_round_up(nq, _BM), 3 * dpad), dtype=torch.bfloat16, device=q.device)
+    b_op = torch.zeros((_round_up(nv, _BN), 3 * dpad), dtype=torch.bfloat16, device=q.device)
+    N.call("xmve_prepare_rows", N.ptr(q), N.F32, nq, d, 1, q.stride(0), None, 0, 0, None, N.ptr(a_op), 3 * dpad, 0,
+           N.OP_X3_QUERY, 1.0, norm_mode, st)
+    N.call("xmve_prepare_rows", N.ptr(v), N.F32, nv, d, 1, v.stride(0), None, 0, 0, None, N.ptr(b_op), 3 * dpad, 0,
+           N.OP_X3_CORPUS, 1.0, norm_mode, st)
+    out = torch.empty((nq, nv), dtype=torch.float32, device=q.device)
+    N.call("xmve_score_store", N.ptr(a_op), nq, 3 * dpad, N.ptr(b_op), nv, 3 * dpad, 1, 3 * dpad, float(alpha),
+           N.ptr(out), nv, st)
+    return out
+
+
+def cal_error(videos, captions, measure='cosine'):
+    """errors[q, v] = -cos(caption q, video v); evaluation.py:17-21."""
+    if measure != 'cosine':
+        raise NotImplementedError("measure=%r is outside the B200 hot path (cosine only)" % (measure,))
+    was_numpy = not torch.is_tensor(captions)
+    return _out(score_matrix(captions, videos, -1.0), was_numpy)
+
+
+def cal_error_batch(videos, captions, measure='cosine', batch_size=2000):
+    """evaluation.py:41-45: the cosine branch does not batch, so this is ``cal_error``."""
+    return cal_error(videos, captions, measure)
+
+
+def cal_simi(captions, videos, measure='cosine'):
+    """+cos(caption, video); evaluation.py:75-79 (captions FIRST here, unlike ``cal_error``)."""
+    if measure != 'cosine':
+        raise NotImplementedError("measure=%r is outside the B200 hot path (cosine only)" % (measure,))
+    was_numpy = not torch.is_tensor(captions)
+    return _out(score_matrix(captions, videos, 1.0), was_numpy)

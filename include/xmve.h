@@ -1,0 +1,196 @@
+/*
+ * xmve.h -- C ABI of the B200-native retrieval scoring library (libxmve.so, sm_100a only).
+ *
+ * The reference (WWWindrunner/Cross-Modal-Video-Engine) is 100 % Python and has no FFI: its
+ * boundary for this path is a set of Python call signatures.  Each entry
+ * point below names the reference lines whose arithmetic it replaces; the Python mirror of the
+ * reference modules (cross-modal-video-engine_b200/{evaluation,validate,metrics,...}.py) binds
+ * them through ctypes.  INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative xmve_status; xmve_last_error() gives a
+ *     thread-local message for the last failure.
+ *   - all data pointers are DEVICE pointers borrowed from the caller (e.g. torch data_ptr());
+ *     nothing is allocated, owned or freed by the library.  `stream` is a cudaStream_t passed as
+ *     void*; work is enqueued on it and the call returns without synchronising.
+ *   - matrices are row-major; `ld` arguments are row strides in ELEMENTS.
+ *   - there is no CPU path: on a device that is not compute capability 10.x every call fails
+ *     with XMVE_ERR_DEVICE.
+ */
+#ifndef XMVE_H_
+#define XMVE_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define XMVE_API __attribute__((visibility("default")))
+#else
+#define XMVE_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum xmve_status {
+  XMVE_OK = 0,
+  XMVE_ERR_ARG = -1,     /* bad argument (null pointer, misaligned, out of range) */
+  XMVE_ERR_DEVICE = -2,  /* no CUDA device / not sm_100 */
+  XMVE_ERR_CUDA = -3,    /* a CUDA runtime / driver call failed */
+  XMVE_ERR_LIMIT = -4    /* a size exceeds what the kernel supports (see each function) */
+} xmve_status;
+
+enum { XMVE_F32 = 0, XMVE_F64 = 1 };
+
+/* operand layouts written by xmve_prepare_rows (how one embedding space is laid out along K) */
+enum {
+  XMVE_OP_X1 = 0,        /* [hi]            K = dpad      bf16(w * x_hat)                        */
+  XMVE_OP_X3_QUERY = 1,  /* [hi | hi | lo]  K = 3 * dpad  split-bf16, query side                  */
+  XMVE_OP_X3_CORPUS = 2  /* [hi | lo | hi]  K = 3 * dpad  split-bf16, corpus side                 */
+};
+
+enum { XMVE_NORM_PLAIN = 0,   /* x / ||x||            (evaluation.py:10-14, no epsilon)          */
+       XMVE_NORM_EPS = 1 };   /* x / max(||x||,1e-12) (torch F.normalize, MultiFusion validate.py:55) */
+
+XMVE_API int xmve_version(void);
+XMVE_API const char* xmve_last_error(void);
+/* Fails unless `device` (or the current device if < 0) is compute capability 10.x. */
+XMVE_API int xmve_device_check(int device);
+/* Number of SMs of the current device (grid sizing); < 0 on error. */
+XMVE_API int xmve_sm_count(void);
+
+/* ---- K1: row normalise + cast (corpus-resident store, query prep) -----------------------------
+ * Replaces evaluation.l2norm (LINAS-engine/evaluation.py:10-14), the re-normalisation inside
+ * cal_error (:19-20), F.normalize(index).float() (MultiFusion/src/validate.py:55) and, with
+ * frames > 1, Combiner.time_process = mean over frames (MultiFusion/src/combiner.py:140-143).
+ *
+ * src       [n, frames, d] fp32/fp64 (src_dtype), row stride src_ld elements (>= frames*d)
+ * raw_out   optional fp32 [n, raw_ld]: the (frame-pooled) raw row is written at column raw_off
+ * norm_out  optional fp64 [n]: ||x||_2 accumulated in double
+ * op_out    optional bf16 [n, op_ld]: operand planes per op_layout written at column op_off,
+ *           plane stride dpad = round_up(d, 64); columns d..dpad of each plane are zero-filled
+ * weight    folded into the operand (per-space fusion weight; 1.0 on the corpus side)
+ */
+XMVE_API int xmve_prepare_rows(const void* src, int src_dtype, int64_t n, int d, int frames, int64_t src_ld,
+                      float* raw_out, int64_t raw_ld, int64_t raw_off,
+                      double* norm_out,
+                      void* op_out, int64_t op_ld, int64_t op_off, int op_layout,
+                      float weight, int norm_mode, void* stream);
+
+/* ---- K2: query x corpus score kernel (tcgen05 / TMEM / TMA, bf16 operands, fp32 accumulate) ----
+ * Replaces np.dot(l2norm(captions), l2norm(videos).T) (LINAS-engine/evaluation.py:21,45,79) and
+ * P @ index.T (MultiFusion/src/validate.py:73,90; inference.py:63).  a_op [nq, a_ld] and
+ * b_op [nv, b_ld] are bf16 operands from xmve_prepare_rows (16-byte aligned, ld % 8 == 0), k is the
+ * contraction length in elements (multiple of 64).  b_row_step > 1 scores every b_row_step-th
+ * corpus row only (a strided TMA view; nv is then the number of sampled rows).
+ *
+ * store : out[q, v] = alpha * <a_q, b_v>   fp32 [nq, out_ld]     (cal_error: alpha = -1)
+ */
+XMVE_API int xmve_score_store(const void* a_op, int64_t nq, int64_t a_ld,
+                     const void* b_op, int64_t nv, int64_t b_ld, int64_t b_row_step, int k,
+                     float alpha, float* out, int64_t out_ld, void* stream);
+
+/* filter: the score matrix never reaches HBM.  Per query row q with window (lo[q], hi[q]]:
+ *   s >  hi[q]            -> count_above[q] += 1                    (hi may be NULL = +inf)
+ *   lo[q] < s <= hi[q]    -> slot = cand_count[q]++ ; if slot < cap:
+ *                            cand_score[q*cap+slot] = s, cand_idx[q*cap+slot] = v
+ * cand_count keeps counting past cap so the caller can detect overflow.  Replaces the full
+ * argsort of every row (LINAS-engine/inference.py:79; MultiFusion/src/validate.py:74,92) as a
+ * streaming threshold top-k, and the rank-of-ground-truth search (util/metrics.py:139-145) as
+ * count_above with a guard band.
+ */
+XMVE_API int xmve_score_filter(const void* a_op, int64_t nq, int64_t a_ld,
+                      const void* b_op, int64_t nv, int64_t b_ld, int k,
+                      const float* lo, const float* hi,
+                      int32_t* count_above, int32_t* cand_count,
+                      float* cand_score, int32_t* cand_idx, int32_t cap, void* stream);
+
+/* ---- order statistics of score rows ------------------------------------------------------------
+ * out[r] = max( kth_largest(row r, j1) - sub , kth_largest(row r, j2) )   (j2 <= 0: first term only)
+ * Row r holds min(counts[r], cols) valid floats (counts == NULL: cols).  Fewer than j valid values
+ * give -inf for that term.  Used for the sampled filter threshold and the candidate pre-filter.
+ */
+XMVE_API int xmve_row_kth(const float* vals, int64_t rows, int64_t cols, int64_t ld, const int32_t* counts,
+                 int32_t j1, float sub, int32_t j2, float* out, void* stream);
+
+/* ---- exact rescoring of candidates in double precision -----------------------------------------
+ * exact[q, c] = sum_s w[s] * <q_s, v_s> / (||q_s|| * ||v_s||)  for candidate c of row q whose
+ * approximate score is >= bound[q] (bound == NULL: all), else -inf.  Raw rows are fp32 (values the
+ * reference keeps in float64 arrays, evaluation.py:102-105); products and sums are in fp64, i.e.
+ * the arithmetic of cal_error on float64 inputs (evaluation.py:19-21) up to rounding order.
+ * space_off[n_space+1] (HOST array) are column offsets into the raw rows, weights[n_space] is a HOST
+ * array, q_norm/v_norm are DEVICE [n_space, n] fp64.  exact[q, c] is written for c < cand_count[q] only.
+ * norm_mode as in xmve_prepare_rows.  Limit: total raw dim <= 8192.
+ */
+XMVE_API int xmve_rescore(const float* q_raw, int64_t nq, int64_t q_ld, const double* q_norm,
+                 const float* v_raw, int64_t nv, int64_t v_ld, const double* v_norm,
+                 int n_space, const int32_t* space_off, const double* weights, int norm_mode,
+                 const float* cand_score, const int32_t* cand_idx, const int32_t* cand_count,
+                 int32_t cap, const float* bound, double* exact, void* stream);
+
+/* ---- final top-k of each row from (score, index) pairs -----------------------------------------
+ * Sorts the valid entries (score > -inf, index != exclude[r]) of row r by (score desc, index asc)
+ * and writes the first k: out_score fp64 [rows, k] (-inf padded), out_idx int64 [rows, k]
+ * (-1 padded; idx + idx_offset otherwise; idx == NULL means idx[r, c] = c), out_valid[r] = number
+ * of valid entries.
+ * Certification (thr != NULL): cert[r] = 1 iff counts[r] <= cols, at least k entries are valid and
+ * kth_score - eps >= thr[r] -- then no corpus item outside the candidate set can belong to the
+ * top-k given |approx - exact| <= eps.  thr_next[r] is the threshold to re-run an uncertified row
+ * with (kth - eps when k entries were found; bound[r] = approximate kth of the retained candidates
+ * - 2 eps after a candidate-list overflow).  Limit: at most 16384 valid entries per row.
+ */
+XMVE_API int xmve_select_topk_i32(const double* score, const int32_t* idx, int64_t rows, int64_t cols,
+                         const int32_t* counts, int64_t idx_offset, const int64_t* exclude, int32_t k,
+                         const float* thr, float eps, const float* bound,
+                         double* out_score, int64_t* out_idx, int32_t* out_valid,
+                         int32_t* cert, float* thr_next, void* stream);
+/* K3: G-way merge of per-shard top-k lists after the all-gather: rows x (G*k) pairs with global
+ * int64 indices -> top-k.  Same ordering rule. */
+XMVE_API int xmve_select_topk_i64(const double* score, const int64_t* idx, int64_t rows, int64_t cols,
+                         const int64_t* exclude, int32_t k,
+                         double* out_score, int64_t* out_idx, int32_t* out_valid, void* stream);
+
+/* ---- exact fp64 score matrix (small problems; the cal_error drop-in on float64 inputs) ----------
+ * out[q, v] = alpha * <a_q, b_v>, a [nq, a_ld], b [nv, b_ld], out [nq, out_ld], all fp64, k columns.
+ * a and b are already normalised (xmve_normalize_f64).  LINAS-engine/evaluation.py:21.
+ */
+XMVE_API int xmve_normalize_f64(const void* src, int src_dtype, int64_t n, int d, int64_t src_ld,
+                       double* dst, int64_t dst_ld, int norm_mode, void* stream);
+XMVE_API int xmve_score_f64(const double* a, int64_t nq, int64_t a_ld, const double* b, int64_t nv, int64_t b_ld,
+                   int k, double alpha, double* out, int64_t out_ld, void* stream);
+
+/* ---- K4: bit-exact rank / metric kernels --------------------------------------------------------
+ * errors is the caller's [n_row, n_col] matrix (fp32/fp64, smaller = better, as cal_error returns).
+ * gt_off[n_query+1], gt_ids[] is a CSR of ground-truth positions per query.
+ * axis = 0: query i is ROW i, memories are columns   (eval_q2m(errors, t2v_gt), util/metrics.py:124-157)
+ * axis = 1: query i is COLUMN i, memories are rows   (eval_q2m(errors.T, v2t_gt), validate.py:22)
+ * ranks[e] (1-based, one per CSR entry) = 1 + #{m : x[m] < x[g]} + #{m < g : x[m] == x[g]}, the
+ * position of g in a stable ascending argsort.  n_entries = gt_off[n_query] and max_gt = the largest
+ * number of entries of any query are passed by the caller (it built the CSR) to avoid a device sync.
+ */
+XMVE_API int xmve_gt_ranks(const void* errors, int dtype, int64_t n_row, int64_t n_col, int64_t ld, int axis,
+                  const int64_t* gt_off, const int32_t* gt_ids, int64_t n_query,
+                  int64_t n_entries, int32_t max_gt, int32_t* ranks, void* stream);
+/* Per-query reduction of the CSR ranks (n_mem = number of memories):
+ *   best[i]   = min rank over the query's GT entries, n_mem + 1 if none   (util/metrics.py:140-147)
+ *   ap[i]     = APScorer(ap_k).score of the label list with the GT entries relevant: ranks sorted
+ *               ascending, ap += j / rank_j in that order, / nr_relevant (basic/metric.py:31-46);
+ *               first_only != 0 marks only the FIRST GT entry (t2v_map, util/metrics.py:72-73)
+ *   recall_counts[0..2] += #{best <= 1, 5, 10}; rank_sum += best; hist[best] += 1 (hist[n_mem+2])
+ */
+XMVE_API int xmve_rank_metrics(const int32_t* ranks, const int64_t* gt_off, int64_t n_query, int64_t n_mem,
+                      int first_only, int ap_k,
+                      int32_t* best, double* ap, int64_t* recall_counts, int64_t* rank_sum,
+                      int32_t* hist, void* stream);
+
+/* ---- norm_score (LINAS-engine/validate.py:7-11) -------------------------------------------------
+ * minmax[0] = min(-E), minmax[1] = max(-E - min) over the whole matrix (two launches inside);
+ * xmve_norm_score_apply writes out = -((-E - min) / max) with the reference's operation order.
+ */
+XMVE_API int xmve_norm_score(const void* errors, int dtype, int64_t n_row, int64_t n_col, int64_t ld,
+                    void* out, int64_t out_ld, double* minmax_scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* XMVE_H_ */

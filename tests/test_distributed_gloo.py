@@ -1,0 +1,49 @@
+"""World-size-2 test of the shard / all-gather / merge plumbing on CPU with the gloo backend.
+The per-shard search itself needs the GPU; here each rank produces its local exact top-k with the oracle
+arithmetic so that the collective path (gather_topk + merge rule) is what is under test."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    from cross_modal_video_engine_b200 import distributed, synth
+    from oracle import linas
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nv, nq, d, k = 1003, 37, 48, 10
+    V, Q = synth.gaussian(1, nv, d).astype(np.float64), synth.gaussian(2, nq, d).astype(np.float64)
+    lo, hi = distributed.shard_range(nv, world, rank)
+    err = linas.cal_error(V[lo:hi], Q)
+    idx = np.argsort(err, axis=1, kind="stable")[:, :k]
+    s_loc = torch.from_numpy(-np.take_along_axis(err, idx, axis=1))
+    i_loc = torch.from_numpy(idx + lo)
+    s_all, i_all = distributed.gather_topk(s_loc, i_loc)
+    ms, mi = distributed.merge_reference(s_all, i_all, k)
+    full = linas.cal_error(V, Q)
+    ref = np.argsort(full, axis=1, kind="stable")[:, :k]
+    ok = np.array_equal(mi.numpy(), ref) and np.allclose(ms.numpy(), -np.take_along_axis(full, ref, axis=1), atol=1e-15)
+    with open(os.path.join(out_dir, "rank%d" % rank), "w") as f:
+        f.write("ok" if ok else "mismatch")
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_and_merge(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"

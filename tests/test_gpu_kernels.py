@@ -1,0 +1,253 @@
+"""Kernel-level parity tests (B200 only), each kernel called through the C ABI (ctypes) and compared with a
+straightforward torch / NumPy statement of the same operation on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def N():
+    from cross_modal_video_engine_b200 import _native
+    _native.require_device()
+    return _native
+
+
+def _rup(x, m):
+    return (x + m - 1) // m * m
+
+
+def _operands(N, nq, nv, d, seed, layout_q=0, layout_v=0):
+    """Random raw rows -> bf16 operands via K1 (x1 or x3 layouts)."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    q = torch.randn((nq, d), generator=g, device="cuda")
+    v = torch.randn((nv, d), generator=g, device="cuda")
+    dpad = _rup(d, 64)
+    planes_q = 1 if layout_q == 0 else 3
+    a = torch.zeros((_rup(nq, 128), planes_q * dpad), dtype=torch.bfloat16, device="cuda")
+    b = torch.zeros((_rup(nv, 256), planes_q * dpad), dtype=torch.bfloat16, device="cuda")
+    st = N.stream_ptr()
+    N.call("xmve_prepare_rows", N.ptr(q), N.F32, nq, d, 1, d, None, 0, 0, None, N.ptr(a), a.stride(0), 0, layout_q, 1.0,
+           0, st)
+    N.call("xmve_prepare_rows", N.ptr(v), N.F32, nv, d, 1, d, None, 0, 0, None, N.ptr(b), b.stride(0), 0, layout_v, 1.0,
+           0, st)
+    return q, v, a, b
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,frames,dtype", [(1000, 1536, 1, torch.float32), (77, 100, 1, torch.float64),
+                                              (300, 640, 8, torch.float32), (5, 2048, 1, torch.float32)])
+def test_prepare_rows(N, n, d, frames, dtype):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    shape = (n, d) if frames == 1 else (n, frames, d)
+    x = (torch.randn(shape, generator=g, device="cuda") * 3).to(dtype)
+    dpad = _rup(d, 64)
+    op = torch.full((n, 3 * dpad + 64), 7.0, dtype=torch.bfloat16, device="cuda")
+    raw = torch.zeros((n, d + 4), dtype=torch.float32, device="cuda")
+    nrm = torch.zeros(n, dtype=torch.float64, device="cuda")
+    N.call("xmve_prepare_rows", N.ptr(x), N.F64 if dtype == torch.float64 else N.F32, n, d, frames, frames * d,
+           N.ptr(raw), raw.stride(0), 4, N.ptr(nrm), N.ptr(op), op.stride(0), 64, N.OP_X3_CORPUS, 0.5, 0,
+           N.stream_ptr())
+    pooled = x.float() if frames == 1 else (x.float().sum(dim=1) / frames)
+    ref_norm = torch.linalg.vector_norm(pooled.double(), dim=1)
+    torch.testing.assert_close(raw[:, 4:4 + d], pooled, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(nrm, torch.linalg.vector_norm(raw[:, 4:4 + d].double(), dim=1), rtol=1e-13, atol=0)
+    y = (0.5 * (raw[:, 4:4 + d].double() / nrm[:, None]).float())
+    hi = y.to(torch.bfloat16)
+    lo = (y - hi.float()).to(torch.bfloat16)
+    assert torch.equal(op[:, 64:64 + d], hi)
+    assert torch.equal(op[:, 64 + dpad:64 + dpad + d], lo)
+    assert torch.equal(op[:, 64 + 2 * dpad:64 + 2 * dpad + d], hi)
+    assert torch.all(op[:, :64] == 7.0)                       # columns before op_off untouched
+    if dpad > d:
+        assert torch.all(op[:, 64 + d:64 + dpad] == 0)        # zero-filled padding of each plane
+    assert float((ref_norm - nrm).abs().max()) < 1e-4
+
+
+SHAPES = [(1000, 1000, 1536), (77, 333, 100), (128, 256, 64), (129, 257, 192), (60, 70000, 2048), (513, 5000, 640)]
+
+
+@pytest.mark.parametrize("nq,nv,d", SHAPES)
+def test_score_store_matches_fp32_matmul_of_the_operands(N, nq, nv, d):
+    q, v, a, b = _operands(N, nq, nv, d, seed=nq + nv)
+    out = torch.full((nq, nv), float("nan"), dtype=torch.float32, device="cuda")
+    N.call("xmve_score_store", N.ptr(a), nq, a.stride(0), N.ptr(b), nv, b.stride(0), 1, a.shape[1], -1.0, N.ptr(out), nv,
+           N.stream_ptr())
+    torch.cuda.synchronize()
+    ref = -(a[:nq].double() @ b[:nv].double().T)
+    err = (out.double() - ref).abs().max().item()
+    assert err < 2e-6, "tcgen05 tile mismatch: max abs err %g" % err      # fp32 accumulation of exact products
+
+
+def test_score_store_x3_split_reaches_fp32_accuracy(N):
+    nq, nv, d = 700, 900, 1536
+    q, v, a, b = _operands(N, nq, nv, d, seed=3, layout_q=N.OP_X3_QUERY, layout_v=N.OP_X3_CORPUS)
+    out = torch.empty((nq, nv), dtype=torch.float32, device="cuda")
+    N.call("xmve_score_store", N.ptr(a), nq, a.stride(0), N.ptr(b), nv, b.stride(0), 1, a.shape[1], 1.0, N.ptr(out), nv,
+           N.stream_ptr())
+    qn = q.double() / torch.linalg.vector_norm(q.double(), dim=1, keepdim=True)
+    vn = v.double() / torch.linalg.vector_norm(v.double(), dim=1, keepdim=True)
+    err = (out.double() - qn @ vn.T).abs().max().item()
+    assert err < 3e-6, err
+
+
+def test_score_store_strided_sample(N):
+    nq, nv, d, step = 200, 10000, 256, 7
+    q, v, a, b = _operands(N, nq, nv, d, seed=9)
+    ns = (nv + step - 1) // step
+    out = torch.empty((nq, ns), dtype=torch.float32, device="cuda")
+    N.call("xmve_score_store", N.ptr(a), nq, a.stride(0), N.ptr(b), ns, b.stride(0), step, d, 1.0, N.ptr(out), ns,
+           N.stream_ptr())
+    ref = a[:nq].double() @ b[:nv:step].double().T
+    assert (out.double() - ref).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("nq,nv,d,use_hi", [(300, 50000, 512, False), (77, 3000, 100, True), (1000, 200000, 128, False)])
+def test_score_filter_window(N, nq, nv, d, use_hi):
+    q, v, a, b = _operands(N, nq, nv, d, seed=11)
+    s = (a[:nq].float() @ b[:nv].float().T)
+    lo = torch.quantile(s[:, :2000], 0.98, dim=1).contiguous()
+    hi = (lo + 0.05).contiguous() if use_hi else None
+    cap = 4096
+    cnt_above = torch.zeros(nq, dtype=torch.int32, device="cuda")
+    cand_count = torch.zeros(nq, dtype=torch.int32, device="cuda")
+    cand_score = torch.zeros((nq, cap), dtype=torch.float32, device="cuda")
+    cand_idx = torch.full((nq, cap), -1, dtype=torch.int32, device="cuda")
+    N.call("xmve_score_filter", N.ptr(a), nq, a.stride(0), N.ptr(b), nv, b.stride(0), d if d % 64 == 0 else _rup(d, 64),
+           N.ptr(lo), N.ptr(hi), N.ptr(cnt_above) if use_hi else None, N.ptr(cand_count), N.ptr(cand_score),
+           N.ptr(cand_idx), cap, N.stream_ptr())
+    torch.cuda.synchronize()
+    margin = 2e-6                       # entries this close to a window edge may fall on either side
+    inside = s > lo[:, None]
+    if use_hi:
+        above = s > hi[:, None]
+        near = ((s - hi[:, None]).abs() < margin).sum(1)
+        assert ((cnt_above - above.sum(1)).abs() <= near).all()
+        inside = inside & ~above
+    exp_count = inside.sum(1)
+    near_lo = ((s - lo[:, None]).abs() < margin).sum(1) + (((s - hi[:, None]).abs() < margin).sum(1) if use_hi else 0)
+    assert ((cand_count - exp_count).abs() <= near_lo).all()
+    assert int(cand_count.max()) <= cap
+    for r in range(0, nq, max(1, nq // 16)):
+        n = int(cand_count[r])
+        got = cand_idx[r, :n].long()
+        assert len(set(got.tolist())) == n                                   # no duplicates
+        torch.testing.assert_close(cand_score[r, :n], s[r, got], rtol=0, atol=2e-6)
+        firm = (s[r] > lo[r] + margin) & ((s[r] < hi[r] - margin) if use_hi else True)
+        assert set(torch.nonzero(firm).flatten().tolist()) <= set(got.tolist())
+
+
+def test_score_filter_counts_past_cap(N):
+    nq, nv, d = 64, 4000, 64
+    q, v, a, b = _operands(N, nq, nv, d, seed=2)
+    lo = torch.full((nq,), -10.0, device="cuda")
+    cap = 128
+    cand_count = torch.zeros(nq, dtype=torch.int32, device="cuda")
+    cand_score = torch.zeros((nq, cap), dtype=torch.float32, device="cuda")
+    cand_idx = torch.zeros((nq, cap), dtype=torch.int32, device="cuda")
+    N.call("xmve_score_filter", N.ptr(a), nq, a.stride(0), N.ptr(b), nv, b.stride(0), 64, N.ptr(lo), None, None,
+           N.ptr(cand_count), N.ptr(cand_score), N.ptr(cand_idx), cap, N.stream_ptr())
+    assert (cand_count == nv).all()                         # every (in-range) column counted, none of the padding
+
+
+@pytest.mark.parametrize("rows,cols", [(50, 10000), (7, 33), (300, 70000)])
+def test_row_kth(N, rows, cols):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((rows, cols), generator=g, device="cuda")
+    x[0, : min(cols, 20)] = 1.25                            # ties
+    counts = torch.randint(1, cols + 1, (rows,), generator=g, device="cuda", dtype=torch.int32)
+    out = torch.empty(rows, device="cuda")
+    j1, j2 = 3, 17
+    N.call("xmve_row_kth", N.ptr(x), rows, cols, cols, N.ptr(counts), j1, 0.5, j2, N.ptr(out), N.stream_ptr())
+    for r in range(rows):
+        n = int(counts[r])
+        srt = torch.sort(x[r, :n], descending=True).values
+        a1 = srt[j1 - 1] - 0.5 if n >= j1 else torch.tensor(float("-inf"), device="cuda")
+        a2 = srt[j2 - 1] if n >= j2 else torch.tensor(float("-inf"), device="cuda")
+        assert out[r].item() == torch.maximum(a1, a2).item()
+
+
+def test_select_topk_and_merge(N):
+    rows, cols, k = 40, 3000, 100
+    g = torch.Generator(device="cuda").manual_seed(8)
+    score = torch.randn((rows, cols), generator=g, device="cuda", dtype=torch.float64)
+    score[:, ::7] = float("-inf")                           # not rescored
+    score[3, 10:40] = 2.0                                   # exact ties -> index order
+    idx = torch.stack([torch.randperm(100000, generator=g, device="cuda")[:cols] for _ in range(rows)]).int()
+    counts = torch.full((rows,), cols - 5, dtype=torch.int32, device="cuda")
+    excl = idx[:, 1].long() + 1000
+    out_s = torch.empty((rows, k), dtype=torch.float64, device="cuda")
+    out_i = torch.empty((rows, k), dtype=torch.int64, device="cuda")
+    valid = torch.empty(rows, dtype=torch.int32, device="cuda")
+    thr = torch.full((rows,), -1.0, device="cuda")
+    cert = torch.empty(rows, dtype=torch.int32, device="cuda")
+    nxt = torch.empty(rows, device="cuda")
+    N.call("xmve_select_topk_i32", N.ptr(score), N.ptr(idx), rows, cols, N.ptr(counts), 1000, N.ptr(excl), k, N.ptr(thr),
+           0.01, None, N.ptr(out_s), N.ptr(out_i), N.ptr(valid), N.ptr(cert), N.ptr(nxt), N.stream_ptr())
+    for r in range(rows):
+        s = score[r, :cols - 5].clone()
+        i = idx[r, :cols - 5].long() + 1000
+        keep = (s > float("-inf")) & (i != excl[r])
+        s, i = s[keep], i[keep]
+        order = sorted(range(len(s)), key=lambda t: (-s[t].item(), i[t].item()))[:k]
+        assert out_i[r].tolist() == [i[t].item() for t in order]
+        assert out_s[r].tolist() == [s[t].item() for t in order]
+        assert int(valid[r]) == int(keep.sum())
+        assert int(cert[r]) == 1 and abs(nxt[r].item() - (out_s[r, k - 1].item() - 0.01)) < 1e-5
+    # K3 merge: split the winners over 4 "shards" and merge them back
+    from cross_modal_video_engine_b200 import engine, distributed
+    sh_s = torch.full((4, rows, k), float("-inf"), dtype=torch.float64, device="cuda")
+    sh_i = torch.full((4, rows, k), -1, dtype=torch.int64, device="cuda")
+    for gi in range(4):
+        part_s, part_i = out_s[:, gi::4], out_i[:, gi::4]
+        sh_s[gi, :, : part_s.shape[1]] = part_s
+        sh_i[gi, :, : part_i.shape[1]] = part_i
+    m_s, m_i = engine.merge_topk(sh_s, sh_i, k)
+    assert torch.equal(m_s, out_s) and torch.equal(m_i, out_i)
+    r_s, r_i = distributed.merge_reference(sh_s, sh_i, k)
+    assert torch.equal(r_s, out_s) and torch.equal(r_i, out_i)
+
+
+def test_rescore_is_fp64_exact(N):
+    import ctypes as C
+    nq, nv, cap = 33, 5000, 64
+    dims = (100, 28)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    q = torch.randn((nq, 128), generator=g, device="cuda")
+    v = torch.randn((nv, 128), generator=g, device="cuda")
+    qn = torch.stack([torch.linalg.vector_norm(q[:, :100].double(), dim=1), torch.linalg.vector_norm(q[:, 100:].double(), dim=1)])
+    vn = torch.stack([torch.linalg.vector_norm(v[:, :100].double(), dim=1), torch.linalg.vector_norm(v[:, 100:].double(), dim=1)])
+    idx = torch.randint(0, nv, (nq, cap), generator=g, device="cuda", dtype=torch.int32)
+    approx = torch.randn((nq, cap), generator=g, device="cuda")
+    count = torch.randint(0, cap + 20, (nq,), generator=g, device="cuda", dtype=torch.int32)
+    bound = torch.zeros(nq, device="cuda")
+    exact = torch.full((nq, cap), 123.0, dtype=torch.float64, device="cuda")
+    off = (C.c_int32 * 3)(0, 100, 128)
+    w = (C.c_double * 2)(0.7, 0.3)
+    N.call("xmve_rescore", N.ptr(q), nq, 128, N.ptr(qn), N.ptr(v), nv, 128, N.ptr(vn), 2, off, w, 0, N.ptr(approx),
+           N.ptr(idx), N.ptr(count), cap, N.ptr(bound), N.ptr(exact), N.stream_ptr())
+    for r in range(nq):
+        n = min(int(count[r]), cap)
+        rows = v[idx[r, :n].long()].double()
+        s = 0.7 * (rows[:, :100] @ q[r, :100].double()) / (qn[0, r] * vn[0, idx[r, :n].long()]) \
+            + 0.3 * (rows[:, 100:] @ q[r, 100:].double()) / (qn[1, r] * vn[1, idx[r, :n].long()])
+        keep = approx[r, :n] >= 0
+        assert torch.all(exact[r, :n][~keep] == float("-inf"))
+        torch.testing.assert_close(exact[r, :n][keep], s[keep], rtol=0, atol=1e-14)
+        assert torch.all(exact[r, n:] == 123.0)             # slots past the count are never written
+
+
+def test_score_f64_and_normalize(N):
+    nq, nv, d = 130, 257, 200
+    g = torch.Generator(device="cuda").manual_seed(6)
+    q = torch.randn((nq, d), generator=g, device="cuda", dtype=torch.float64)
+    v = torch.randn((nv, d), generator=g, device="cuda")
+    qn = torch.empty((nq, d), dtype=torch.float64, device="cuda")
+    vn = torch.empty((nv, d), dtype=torch.float64, device="cuda")
+    N.call("xmve_normalize_f64", N.ptr(q), N.F64, nq, d, d, N.ptr(qn), d, 0, N.stream_ptr())
+    N.call("xmve_normalize_f64", N.ptr(v), N.F32, nv, d, d, N.ptr(vn), d, 0, N.stream_ptr())
+    torch.testing.assert_close(qn, q / torch.linalg.vector_norm(q, dim=1, keepdim=True), rtol=0, atol=2e-16)
+    out = torch.empty((nq, nv), dtype=torch.float64, device="cuda")
+    N.call("xmve_score_f64", N.ptr(qn), nq, d, N.ptr(vn), nv, d, d, -1.0, N.ptr(out), nv, N.stream_ptr())
+    torch.testing.assert_close(out, -(qn @ vn.T), rtol=0, atol=1e-14)

@@ -205,11 +205,12 @@ class CorpusStore:
                None, 0.0, None, N.ptr(out_s), N.ptr(out_i), None, None, None, st)
         return out_s, out_i
 
-    def plan(self, k):
-        """Sampling step, order statistics and candidate capacity for a top-``k`` search of this shard."""
-        n_s = min(self.n, max(8192, min(65536, self.n // 128)))
-        step = max(1, self.n // n_s)
-        n_s = (self.n + step - 1) // step
+    def plan(self, k, n=None):
+        """Sampling step, order statistics and candidate capacity for a top-``k`` search of ``n`` rows."""
+        n = self.n if n is None else int(n)
+        n_s = min(n, max(8192, min(65536, n // 128)))
+        step = max(1, n // max(n_s, 1))
+        n_s = (n + step - 1) // step
         lam = k / step
         j = int(math.ceil(lam + 5.5 * math.sqrt(lam) + 4))
         cap = 1 << max(11, int(math.ceil(math.log2(8 * step * j))))

@@ -109,7 +109,7 @@ def test_score_filter_window(N, nq, nv, d, use_hi):
     s = (a[:nq].float() @ b[:nv].float().T)
     lo = torch.quantile(s[:, :2000], 0.98, dim=1).contiguous()
     hi = (lo + 0.05).contiguous() if use_hi else None
-    cap = 4096
+    cap = 8192
     cnt_above = torch.zeros(nq, dtype=torch.int32, device="cuda")
     cand_count = torch.zeros(nq, dtype=torch.int32, device="cuda")
     cand_score = torch.zeros((nq, cap), dtype=torch.float32, device="cuda")

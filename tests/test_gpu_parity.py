@@ -54,10 +54,10 @@ def test_cal_error_f32_within_tolerance(X, manifest, name):
     errors = X.evaluation.cal_error(V, Q)                      # fp32 in -> tcgen05 split-bf16 path, fp32 out
     assert errors.dtype == np.float32
     ref = linas.cal_error(V.astype(np.float64), Q.astype(np.float64))
-    assert np.abs(errors - ref).max() < 3e-6
+    assert np.abs(errors - ref).max() < 2e-5                    # split-bf16 bound: ~3 * 2^-18 * sum |q_i v_i|
     big = np.abs(ref) > 1e-2                                    # relative 1e-3 is ill-posed for scores near 0
     assert (np.abs(errors - ref)[big] / np.abs(ref)[big]).max() < 1e-3
-    np.testing.assert_allclose(errors[:8, :8], g["errors_head_f32"], rtol=0, atol=3e-6)
+    np.testing.assert_allclose(errors[:8, :8], g["errors_head_f32"], rtol=0, atol=2e-5)
     simi = X.evaluation.cal_simi(Q, V)                          # swapped argument order, + sign
     np.testing.assert_allclose(simi, -errors, rtol=0, atol=0)
     np.testing.assert_allclose(X.evaluation.cal_error_batch(V, Q), errors, rtol=0, atol=0)
@@ -171,7 +171,7 @@ def test_search_recovers_when_threshold_is_wrong(X):
     rng = np.random.default_rng(3)
     V = rng.standard_normal((nv, d)).astype(np.float32)
     Q = rng.standard_normal((nq, d)).astype(np.float32)
-    step = X.engine.CorpusStore(nv, (d,)).plan(k)["step"]
+    step = X.engine.CorpusStore(nv, (d,)).plan(k, n=nv)["step"]
     grid = rng.permutation(np.arange(0, nv, step))[: 30 * nq].reshape(nq, 30)
     for qi in range(nq):
         V[grid[qi]] = Q[qi] + 0.3 * rng.standard_normal((30, d)).astype(np.float32)

@@ -177,6 +177,7 @@ class ClockSampler:
             out["sm_max_mhz"] = mx
         out["reasons"] = sorted(reasons)
         out["samples"] = len(clocks)
+        out["sm_mhz_min_max"] = [clocks[0], clocks[-1]] if clocks else None
         return out
 
 

@@ -172,6 +172,16 @@ __device__ __forceinline__ void tma_load_2d_pair(const void* desc, uint64_t* bar
         "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_pair_hint(const void* desc, uint64_t* bar, void* smem_dst, int32_t c0,
+                                                      int32_t c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0),
+        "r"(c1), "l"(hint)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                "r"(ncols)

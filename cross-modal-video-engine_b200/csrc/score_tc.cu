@@ -220,8 +220,10 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
               // both CTAs' bytes are accounted on the leader's barrier, which expects the pair's total
               if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
               else ptx::mbar_arrive_remote(&full_bar[stage], 0);
-              ptx::tma_load_2d_pair(&tm_a, &full_bar[stage], sa, kb * BK, a_row);
-              ptx::tma_load_2d_pair(&tm_b, &full_bar[stage], sa + A_BYTES, kb * BK, b_row);
+              if (p.hint_a) ptx::tma_load_2d_pair_hint(&tm_a, &full_bar[stage], sa, kb * BK, a_row, p.hint_a);
+              else ptx::tma_load_2d_pair(&tm_a, &full_bar[stage], sa, kb * BK, a_row);
+              if (p.hint_b) ptx::tma_load_2d_pair_hint(&tm_b, &full_bar[stage], sa + A_BYTES, kb * BK, b_row, p.hint_b);
+              else ptx::tma_load_2d_pair(&tm_b, &full_bar[stage], sa + A_BYTES, kb * BK, b_row);
             } else {
               ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
               if (p.hint_a) ptx::tma_load_2d_hint(&tm_a, &full_bar[stage], sa, kb * BK, a_row, p.hint_a);
@@ -353,8 +355,10 @@ int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int64_t k
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
+  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  if (const char* env = getenv("XMVE_L2PROMO")) promo = static_cast<CUtensorMapL2promotion>(atoi(env) & 3);
   CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(XMVE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld k=%lld ld=%lld", static_cast<int>(r),

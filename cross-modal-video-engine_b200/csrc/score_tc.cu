@@ -5,21 +5,26 @@
 // Persistent, warp-specialised, one CTA per SM:
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B swizzle, multi-stage smem ring)
 //   warp 1      MMA issuer     (tcgen05.mma, fp32 accumulators in TMEM; one elected thread)
-//   warp 2      TMEM allocator (512 columns = two 256-column accumulator stages)
-//   warps 4-7   epilogue       (tcgen05.ld, one query row per thread)
-// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warp 2      TMEM allocator (512 columns = two 256-column accumulator slots)
+//   warps 4..   epilogue       (tcgen05.ld, one query row per thread)
 // Two epilogues share the main loop:
 //   STORE   out = alpha * S                                   (cal_error / sampling pass)
 //   FILTER  per-row window (lo, hi]: count scores above hi, append (score, index) of scores inside
 //           the window to a per-row candidate list -- the score matrix never reaches HBM.
 //
-// Two tile shapes:
-//   PAIR (default)  two CTAs of a cluster drive one tcgen05.mma.cta_group::2 of 256 x 256 x 16: each CTA
-//                   holds its 128 query rows and HALF of the 256-row corpus tile, so the shared-memory and
-//                   L2 traffic per flop drop by a third against the single-CTA tile (32 KB instead of 48 KB
-//                   per SM and k-block) -- the single-CTA kernel sits at the shared-memory bandwidth wall
-//                   (96 B/clk of operand reads + 96 B/clk of TMA writes against 128 B/clk).
-//   SINGLE          one CTA, 128 x 256 x 16 (cta_group::1); kept for comparison (XMVE_CTA_PAIR=0).
+// Tile shapes (XMVE_TILE = 0 | 1 | 2 overrides the choice made in launch()):
+//   SINGLE (0)  one CTA, tcgen05.mma.cta_group::1 of 128 x 256 x 16, two accumulator slots double-buffered (the
+//               epilogue of tile i overlaps the MMAs of tile i+1).  Chosen when the corpus streams from HBM: it
+//               reads every corpus line from DRAM once (95 % L2 hits) where the pair kernels re-fetch ~10x.
+//   PAIR (1)    two CTAs of a cluster drive one tcgen05.mma.cta_group::2 of 256 x 256 x 16: each CTA stages its
+//               128 query rows and HALF of the corpus tile (32 KB instead of 48 KB per SM and k-block).
+//   WIDE (2)    a CTA pair computes 256 queries x 512 corpus rows: per k-block each CTA stages its 128 query rows
+//               ONCE plus its halves of TWO corpus sub-tiles and the leader issues two cta_group::2 MMA chains that
+//               share the query operand (48 KB per SM per 1024 tensor clocks -- the fewest operand bytes per flop).
+//               Both accumulator slots belong to one tile, so the epilogue is not overlapped; 8 warps run it.
+//               Chosen when both operands are L2-resident (fastest there: +11 % over SINGLE, sustained).
+// The kernel runs at the 1 kW power cap (SM clock 1.1-1.4 GHz under load), so operand bytes moved per flop
+// decide the sustained rate, not tensor-pipe occupancy (profiles/r1_tile_schedule_sweep.md).
 //
 // Work is cut into units of ONE corpus tile x a group of query tiles, walked query-tile-major, inside
 // super-blocks of the query operand sized for L2 (see plan_schedule()).
@@ -37,32 +42,36 @@ namespace xmve {
 namespace {
 
 constexpr int BM = 128;              // query rows per CTA tile (TMEM lanes)
-constexpr int BN = 256;              // corpus rows per tile (TMEM columns per accumulator stage)
+constexpr int BN = 256;              // corpus rows per accumulator slot (TMEM columns)
 constexpr int BK = 64;               // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int ACC_STAGES = 2;
-constexpr int THREADS = 256;
+constexpr int ACC_SLOTS = 2;
 constexpr int EPI_WARP0 = 4;
-constexpr int TMEM_COLS = ACC_STAGES * BN;   // 512
+constexpr int TMEM_COLS = ACC_SLOTS * BN;    // 512
 constexpr int A_BYTES = BM * BK * 2;         // 16 KB
 
 enum { MODE_STORE = 0, MODE_FILTER = 1 };
 
-template <bool PAIR>
+// NB = 256-column corpus sub-tiles per tile (1: slots double-buffer, 2: both slots form one tile)
+template <bool PAIR, int NB>
 struct Cfg {
-  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;            // corpus rows this CTA stages per k-block
-  static constexpr int B_BYTES = B_ROWS * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;        // 32 KB (pair) / 48 KB (single)
-  static constexpr int STAGES = PAIR ? 6 : 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(NB == 1 || (NB == 2 && PAIR), "the wide tile exists for CTA pairs only");
   static constexpr int CTAS = PAIR ? 2 : 1;
-  static constexpr int TILE_M = BM * CTAS;                     // query rows per MMA tile
+  static constexpr int B_ROWS = BN / CTAS;                     // rows of one sub-tile this CTA stages per k-block
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + NB * B_BYTES;   // 48 KB (wide) / 32 KB (pair) / 48 KB (single)
+  static constexpr int STAGES = PAIR ? (NB == 2 ? 4 : 6) : 4;
+  static constexpr int THREADS = 128 + 128 * NB;               // 4 control warps + 4 epilogue warps per sub-tile
+  static constexpr int PARK_BYTES = (THREADS - 128) * 8 * 8;   // STG (score, index) pairs per epilogue thread
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + PARK_BYTES;
+  static constexpr int TILE_M = BM * CTAS;                     // query rows per tile
+  static constexpr int TILE_N = BN * NB;                       // corpus rows per tile
 };
 
 struct Params {
   int64_t nq, nv;
   int k_blocks;
-  int m_tiles, n_tiles, m_group, n_mgroups, sb_tiles;   // m_tiles in units of TILE_M rows
+  int m_tiles, n_tiles, m_group, n_mgroups, sb_tiles;   // m_tiles in units of TILE_M rows, n_tiles of TILE_N
   int64_t n_units, units_per_sb;
   uint64_t hint_a, hint_b;
   // STORE
@@ -104,74 +113,129 @@ __device__ __forceinline__ Unit decode_unit(const Params& p, int64_t u, int work
   return x;
 }
 
-// One 128-row x 256-column accumulator stage -> STORE or FILTER.  `row` is this thread's query row.
-template <int MODE>
-__device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t taddr, int64_t row, int64_t col0, float lo,
-                                              float hi, int& cnt) {
-  const bool row_ok = row < p.nq;
-#pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    uint32_t v[32];
-    ptx::tmem_ld_32x32(taddr + c * 32, v);
-    ptx::tmem_ld_wait();
-    const int64_t col = col0 + c * 32;
-    if (MODE == MODE_STORE) {
-      if (row_ok) {
-        float* dst = p.out + row * p.out_ld + col;
-        if (p.vec_ok && col + 32 <= p.nv) {
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// Candidates found while a TMEM slot is drained are parked in a small per-thread shared-memory list and
+// appended to the row's global list AFTER the slot has been handed back to the MMA warp: one atomicAdd per
+// thread and tile, issued by all lanes of the warp together, instead of one blocking atomic per candidate
+// inside the divergent scan (which cost 25 % of the kernel at ~1e-3 candidates per score; profiles/).
+constexpr int STG = 8;                                   // parked candidates per thread
+__device__ __noinline__ void flush_parked(int32_t* cand_count, float* cand_score, int32_t* cand_idx, int cap,
+                                          int64_t row, const uint2* stg, int n) {
+  const int base = atomicAdd(&cand_count[row], n);
+  for (int e = 0; e < n; ++e) {
+    const int slot = base + e;
+    if (slot < cap) {
+      const uint2 c = stg[e];
+      cand_score[row * cap + slot] = __uint_as_float(c.x);
+      cand_idx[row * cap + slot] = static_cast<int32_t>(c.y);
+    }
+  }
+}
+
+struct RowState {
+  int64_t row;
+  float lo, hi;
+  int above;         // scores above hi (count_above)
+  int n;             // parked candidates
+  uint2* stg;
+};
+
+__device__ __forceinline__ void filter_one(const Params& p, RowState& st, float s, int32_t col) {
+  if (s > st.hi) {
+    ++st.above;
+  } else {
+    if (st.n == STG) {
+      flush_parked(p.cand_count, p.cand_score, p.cand_idx, p.cap, st.row, st.stg, st.n);
+      st.n = 0;
+    }
+    st.stg[st.n++] = make_uint2(__float_as_uint(s), static_cast<uint32_t>(col));
+  }
+}
+
+// 32 consecutive scores of one query row: a tree of 3-input maxima decides whether anything enters the
+// window (rare); only the 3-element groups whose maximum does are examined element by element.
+__device__ __forceinline__ void filter_chunk(const Params& p, const uint32_t (&v)[32], RowState& st, int64_t col) {
+  float m[11];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 w = make_float4(p.alpha * __uint_as_float(v[i]), p.alpha * __uint_as_float(v[i + 1]),
-                                   p.alpha * __uint_as_float(v[i + 2]), p.alpha * __uint_as_float(v[i + 3]));
-            *reinterpret_cast<float4*>(dst + i) = w;
-          }
-        } else {
+  for (int g = 0; g < 10; ++g)
+    m[g] = max3(__uint_as_float(v[3 * g]), __uint_as_float(v[3 * g + 1]), __uint_as_float(v[3 * g + 2]));
+  m[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+  const float a = max3(m[0], m[1], m[2]), b = max3(m[3], m[4], m[5]), c = max3(m[6], m[7], m[8]);
+  if (max3(max3(a, b, c), m[9], m[10]) > st.lo) {
+    const int64_t left = p.nv - col;                     // columns of this chunk inside the corpus
+    const int lim = left < 32 ? static_cast<int>(left) : 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col + i < p.nv) dst[i] = p.alpha * __uint_as_float(v[i]);
-        }
-      }
-    } else {
-      float m = __uint_as_float(v[0]);
+    for (int g = 0; g < 11; ++g) {
+      if (m[g] > st.lo) {
 #pragma unroll
-      for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-      if (m > lo) {                                      // rare: at least one score enters the window
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int e = 0; e < (g < 10 ? 3 : 2); ++e) {
+          const int i = 3 * g + e;
           const float s = __uint_as_float(v[i]);
-          if (s > lo && col + i < p.nv) {
-            if (s > hi) {
-              ++cnt;
-            } else {
-              const int slot = atomicAdd(&p.cand_count[row], 1);
-              if (slot < p.cap) {
-                p.cand_score[row * p.cap + slot] = s;
-                p.cand_idx[row * p.cap + slot] = static_cast<int32_t>(col + i);
-              }
-            }
-          }
+          if (s > st.lo && i < lim) filter_one(p, st, s, static_cast<int32_t>(col) + i);
         }
       }
     }
   }
 }
 
-template <int MODE, bool PAIR>
+__device__ __forceinline__ void store_chunk(const Params& p, const uint32_t (&v)[32], int64_t row, int64_t col) {
+  if (row >= p.nq) return;
+  float* dst = p.out + row * p.out_ld + col;
+  if (p.vec_ok && col + 32 <= p.nv) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float4 w = make_float4(p.alpha * __uint_as_float(v[i]), p.alpha * __uint_as_float(v[i + 1]),
+                             p.alpha * __uint_as_float(v[i + 2]), p.alpha * __uint_as_float(v[i + 3]));
+      *reinterpret_cast<float4*>(dst + i) = w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (col + i < p.nv) dst[i] = p.alpha * __uint_as_float(v[i]);
+  }
+}
+
+// One 128-row x 256-column accumulator slot -> STORE or FILTER (this thread owns query row st.row).  The TMEM
+// loads are software-pipelined: chunk c+1 is in flight while chunk c is examined.
+template <int MODE>
+__device__ __forceinline__ void epilogue_slot(const Params& p, uint32_t taddr, RowState& st, int64_t col0) {
+  uint32_t v0[32], v1[32];
+  ptx::tmem_ld_32x32(taddr, v0);
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; c += 2) {
+    ptx::tmem_ld_wait();
+    ptx::tmem_ld_32x32(taddr + (c + 1) * 32, v1);
+    if (MODE == MODE_STORE) store_chunk(p, v0, st.row, col0 + c * 32);
+    else filter_chunk(p, v0, st, col0 + c * 32);
+    ptx::tmem_ld_wait();
+    if (c + 2 < BN / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, v0);
+    if (MODE == MODE_STORE) store_chunk(p, v1, st.row, col0 + (c + 1) * 32);
+    else filter_chunk(p, v1, st, col0 + (c + 1) * 32);
+  }
+}
+
+template <int MODE, bool PAIR, int NB>
 __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const Params& p) {
-  using C = Cfg<PAIR>;
+  using C = Cfg<PAIR, NB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tfull_bar = empty_bar + C::STAGES;
-  uint64_t* tempty_bar = tfull_bar + ACC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + ACC_STAGES);
+  uint64_t* tempty_bar = tfull_bar + ACC_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + ACC_SLOTS);
+  uint2* park = reinterpret_cast<uint2*>(smem + C::STAGES * C::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;   // warp-uniform
   const int lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0;      // 0 = leader (issues the pair's MMAs)
-  const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int n_workers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_a);
@@ -182,7 +246,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
       ptx::mbar_init(&full_bar[s], C::CTAS);                   // one producer arrival per CTA of the pair
       ptx::mbar_init(&empty_bar[s], 1);                        // one tcgen05.commit
     }
-    for (int a = 0; a < ACC_STAGES; ++a) {
+    for (int a = 0; a < ACC_SLOTS; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);                        // one tcgen05.commit
       ptx::mbar_init(&tempty_bar[a], 4 * C::CTAS);             // one arrival per epilogue warp (of both CTAs)
     }
@@ -210,26 +274,32 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
       uint32_t phase = 0;
       for (int64_t u = worker; u < p.n_units; u += n_workers) {
         const Unit un = decode_unit(p, u, worker);
-        const int b_row = un.t * BN + static_cast<int>(rank) * C::B_ROWS;
+        const int b_row = un.t * C::TILE_N + static_cast<int>(rank) * C::B_ROWS;
         for (int i = 0; i < un.len; ++i) {
           const int a_row = un.mt(i) * C::TILE_M + static_cast<int>(rank) * BM;
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * C::STAGE_BYTES;
+            const int kc = kb * BK;
             if (PAIR) {
               // both CTAs' bytes are accounted on the leader's barrier, which expects the pair's total
               if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
               else ptx::mbar_arrive_remote(&full_bar[stage], 0);
-              if (p.hint_a) ptx::tma_load_2d_pair_hint(&tm_a, &full_bar[stage], sa, kb * BK, a_row, p.hint_a);
-              else ptx::tma_load_2d_pair(&tm_a, &full_bar[stage], sa, kb * BK, a_row);
-              if (p.hint_b) ptx::tma_load_2d_pair_hint(&tm_b, &full_bar[stage], sa + A_BYTES, kb * BK, b_row, p.hint_b);
-              else ptx::tma_load_2d_pair(&tm_b, &full_bar[stage], sa + A_BYTES, kb * BK, b_row);
+              if (p.hint_a) ptx::tma_load_2d_pair_hint(&tm_a, &full_bar[stage], sa, kc, a_row, p.hint_a);
+              else ptx::tma_load_2d_pair(&tm_a, &full_bar[stage], sa, kc, a_row);
+#pragma unroll
+              for (int j = 0; j < NB; ++j) {
+                uint8_t* sb = sa + A_BYTES + j * C::B_BYTES;
+                if (p.hint_b)
+                  ptx::tma_load_2d_pair_hint(&tm_b, &full_bar[stage], sb, kc, b_row + j * BN, p.hint_b);
+                else ptx::tma_load_2d_pair(&tm_b, &full_bar[stage], sb, kc, b_row + j * BN);
+              }
             } else {
               ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-              if (p.hint_a) ptx::tma_load_2d_hint(&tm_a, &full_bar[stage], sa, kb * BK, a_row, p.hint_a);
-              else ptx::tma_load_2d(&tm_a, &full_bar[stage], sa, kb * BK, a_row);
-              if (p.hint_b) ptx::tma_load_2d_hint(&tm_b, &full_bar[stage], sa + A_BYTES, kb * BK, b_row, p.hint_b);
-              else ptx::tma_load_2d(&tm_b, &full_bar[stage], sa + A_BYTES, kb * BK, b_row);
+              if (p.hint_a) ptx::tma_load_2d_hint(&tm_a, &full_bar[stage], sa, kc, a_row, p.hint_a);
+              else ptx::tma_load_2d(&tm_a, &full_bar[stage], sa, kc, a_row);
+              if (p.hint_b) ptx::tma_load_2d_hint(&tm_b, &full_bar[stage], sa + A_BYTES, kc, b_row, p.hint_b);
+              else ptx::tma_load_2d(&tm_b, &full_bar[stage], sa + A_BYTES, kc, b_row);
             }
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
@@ -245,61 +315,84 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
       for (int64_t u = worker; u < p.n_units; u += n_workers) {
         const Unit un = decode_unit(p, u, worker);
         for (int i = 0; i < un.len; ++i) {
-          ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);     // epilogue(s) have drained this accumulator
-          ptx::tc_fence_after_sync();
-          const uint32_t tmem_d = tmem_base + acc * BN;
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             ptx::mbar_wait(&full_bar[stage], phase);           // TMA bytes (of both CTAs) have landed
             ptx::tc_fence_after_sync();
             const uint32_t sa = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
             const uint64_t da = ptx::smem_desc_k_sw128(sa);
-            const uint64_t db = ptx::smem_desc_k_sw128(sa + A_BYTES);
 #pragma unroll
-            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-              // +32 bytes along K inside the 128-byte swizzle row = +2 in the (addr >> 4) field
-              if (PAIR) ptx::umma_bf16_pair(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
-              else ptx::umma_bf16(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
+            for (int j = 0; j < NB; ++j) {
+              const int slot = NB == 1 ? acc : j;
+              if (kb == 0) {
+                ptx::mbar_wait(&tempty_bar[slot], acc_phase ^ 1);   // the epilogue warps have drained this slot
+                ptx::tc_fence_after_sync();
+              }
+              const uint32_t tmem_d = tmem_base + slot * BN;
+              const uint64_t db = ptx::smem_desc_k_sw128(sa + A_BYTES + j * C::B_BYTES);
+#pragma unroll
+              for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                // +32 bytes along K inside the 128-byte swizzle row = +2 in the (addr >> 4) field
+                if (PAIR) ptx::umma_bf16_pair(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
+                else ptx::umma_bf16(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
+              }
             }
             // frees the smem slot (in both CTAs) when the MMAs retire
             if (PAIR) ptx::umma_commit_pair(&empty_bar[stage], 0x3);
             else ptx::umma_commit(&empty_bar[stage]);
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
-          if (PAIR) ptx::umma_commit_pair(&tfull_bar[acc], 0x3);  // accumulator complete -> both epilogues
-          else ptx::umma_commit(&tfull_bar[acc]);
-          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {                        // accumulator(s) complete -> epilogue warps
+            const int slot = NB == 1 ? acc : j;
+            if (PAIR) ptx::umma_commit_pair(&tfull_bar[slot], 0x3);
+            else ptx::umma_commit(&tfull_bar[slot]);
+          }
+          if (NB == 2) acc_phase ^= 1;
+          else if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
         }
       }
     }
   } else if (warp >= EPI_WARP0) {
     // ================================ epilogue ====================================
     const int quarter = warp & 3;                              // TMEM lane quarter this warp may read
+    const int sub = (warp - EPI_WARP0) >> 2;                   // sub-tile (accumulator slot) of the wide tile
     const int row_in_tile = static_cast<int>(rank) * BM + quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    RowState st;
+    st.stg = park + (threadIdx.x - EPI_WARP0 * 32) * STG;
+    st.n = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t u = worker; u < p.n_units; u += n_workers) {
       const Unit un = decode_unit(p, u, worker);
-      const int64_t col0 = static_cast<int64_t>(un.t) * BN;
+      const int64_t col0 = static_cast<int64_t>(un.t) * C::TILE_N + sub * BN;
       for (int i = 0; i < un.len; ++i) {
-        const int64_t row = static_cast<int64_t>(un.mt(i)) * C::TILE_M + row_in_tile;
-        float lo = __int_as_float(0x7f800000), hi = __int_as_float(0x7f800000);
-        int cnt = 0;
-        if (MODE == MODE_FILTER && row < p.nq) {
-          lo = p.lo[row];
-          if (p.hi != nullptr) hi = p.hi[row];
+        const int slot = NB == 1 ? acc : sub;
+        st.row = static_cast<int64_t>(un.mt(i)) * C::TILE_M + row_in_tile;
+        st.lo = st.hi = __int_as_float(0x7f800000);            // rows past nq: nothing enters the window
+        st.above = 0;
+        if (MODE == MODE_FILTER && st.row < p.nq) {
+          st.lo = p.lo[st.row];
+          if (p.hi != nullptr) st.hi = p.hi[st.row];
         }
-        ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+        ptx::mbar_wait(&tfull_bar[slot], acc_phase);
         ptx::tc_fence_after_sync();
-        epilogue_tile<MODE>(p, tmem_base + lane_addr + acc * BN, row, col0, lo, hi, cnt);
+        epilogue_slot<MODE>(p, tmem_base + lane_addr + slot * BN, st, col0);
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) {                                       // one arrival per warp on the LEADER's barrier
-          if (PAIR && rank != 0) ptx::mbar_arrive_remote(&tempty_bar[acc], 0);
-          else ptx::mbar_arrive(&tempty_bar[acc]);
+          if (PAIR && rank != 0) ptx::mbar_arrive_remote(&tempty_bar[slot], 0);
+          else ptx::mbar_arrive(&tempty_bar[slot]);
         }
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-        if (MODE == MODE_FILTER && cnt != 0 && p.count_above != nullptr) atomicAdd(&p.count_above[row], cnt);
+        if (NB == 2) acc_phase ^= 1;
+        else if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
+        if (MODE == MODE_FILTER) {                             // the slot is already back with the MMA warp
+          if (st.n != 0) {
+            flush_parked(p.cand_count, p.cand_score, p.cand_idx, p.cap, st.row, st.stg, st.n);
+            st.n = 0;
+          }
+          if (st.above != 0 && p.count_above != nullptr) atomicAdd(&p.count_above[st.row], st.above);
+        }
       }
     }
   }
@@ -315,15 +408,21 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(Cfg<false, 1>::THREADS, 1)
 score_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
-  score_body<MODE, false>(tm_a, tm_b, p);
+  score_body<MODE, false, 1>(tm_a, tm_b, p);
 }
 
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<true, 1>::THREADS, 1)
 score_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
-  score_body<MODE, true>(tm_a, tm_b, p);
+  score_body<MODE, true, 1>(tm_a, tm_b, p);
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<true, 2>::THREADS, 1)
+score_wide_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
+  score_body<MODE, true, 2>(tm_a, tm_b, p);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -375,7 +474,7 @@ int check_operands(const void* a_op, int64_t nq, int64_t a_ld, const void* b_op,
                "score: row strides must be >= k and multiples of 8 elements");
   XMVE_REQUIRE(aligned16(a_op) && aligned16(b_op), "score: operands must be 16-byte aligned");
   XMVE_REQUIRE(b_row_step >= 1, "score: b_row_step must be >= 1");
-  if (nv > (int64_t(1) << 31) - BN || nq > (int64_t(1) << 31) - BM)
+  if (nv > (int64_t(1) << 31) - 2 * BN || nq > (int64_t(1) << 31) - 2 * BM)
     return fail(XMVE_ERR_LIMIT, "score: more than 2^31 rows");
   return XMVE_OK;
 }
@@ -385,9 +484,9 @@ int check_operands(const void* a_op, int64_t nq, int64_t a_ld, const void* b_op,
 //   (query operand of the current super-block) + (corpus tiles live across the concurrent workers).
 // Queries are therefore walked in super-blocks of <= ~16 MB of operand, and inside a super-block
 // several workers share each corpus tile (m_group query tiles each).
-void plan_schedule(Params& p, int tile_m, int k, int workers) {
+void plan_schedule(Params& p, int tile_m, int tile_n, int k, int workers) {
   p.m_tiles = static_cast<int>((p.nq + tile_m - 1) / tile_m);
-  p.n_tiles = static_cast<int>((p.nv + BN - 1) / BN);
+  p.n_tiles = static_cast<int>((p.nv + tile_n - 1) / tile_n);
   const int64_t a_tile_bytes = static_cast<int64_t>(tile_m) * k * 2;
   int64_t sb_mb = 16;
   if (const char* env = getenv("XMVE_SB_MB")) sb_mb = atoi(env);
@@ -407,16 +506,16 @@ void plan_schedule(Params& p, int tile_m, int k, int workers) {
   p.n_mgroups = static_cast<int>((sbt + mg - 1) / mg);
   p.units_per_sb = static_cast<int64_t>(p.n_tiles) * p.n_mgroups;
   p.n_units = p.units_per_sb * n_sb;
-  static const uint64_t hints[3] = {0, ptx::L2_EVICT_LAST, ptx::L2_EVICT_FIRST};
+  static const uint64_t hints[4] = {0, ptx::L2_EVICT_LAST, ptx::L2_EVICT_FIRST, ptx::L2_EVICT_NORMAL};
   p.hint_a = p.hint_b = 0;
-  if (const char* env = getenv("XMVE_HINT_A")) p.hint_a = hints[atoi(env) % 3];
-  if (const char* env = getenv("XMVE_HINT_B")) p.hint_b = hints[atoi(env) % 3];
+  if (const char* env = getenv("XMVE_HINT_A")) p.hint_a = hints[atoi(env) & 3];
+  if (const char* env = getenv("XMVE_HINT_B")) p.hint_b = hints[atoi(env) & 3];
 }
 
-template <int MODE, bool PAIR>
+template <int MODE, bool PAIR, int NB>
 int launch_cfg(const void* a_op, int64_t nq, int64_t a_ld, const void* b_op, int64_t nv, int64_t b_ld,
                int64_t b_row_step, int k, Params p, cudaStream_t stream) {
-  using C = Cfg<PAIR>;
+  using C = Cfg<PAIR, NB>;
   CUtensorMap tm_a, tm_b;
   int s = make_operand_map(&tm_a, a_op, nq, k, a_ld, BM);
   if (s != XMVE_OK) return s;
@@ -428,34 +527,35 @@ int launch_cfg(const void* a_op, int64_t nq, int64_t a_ld, const void* b_op, int
   p.nq = nq;
   p.nv = nv;
   p.k_blocks = k / BK;
-  plan_schedule(p, C::TILE_M, k, workers_max);
+  plan_schedule(p, C::TILE_M, C::TILE_N, k, workers_max);
   const int workers = static_cast<int>(p.n_units < workers_max ? p.n_units : workers_max);
   const int grid = workers * C::CTAS;
-  static bool attr_set = false;                               // one flag per <MODE, PAIR> instantiation
-  if (PAIR) {
-    if (!attr_set) {
-      XMVE_CUDA(cudaFuncSetAttribute(score_pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     C::SMEM_BYTES));
-      attr_set = true;
-    }
-    score_pair_kernel<MODE><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tm_a, tm_b, p);
-  } else {
-    if (!attr_set) {
-      XMVE_CUDA(cudaFuncSetAttribute(score_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-      attr_set = true;
-    }
-    score_kernel<MODE><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tm_a, tm_b, p);
+  void (*kern)(const CUtensorMap, const CUtensorMap, const Params) =
+      !PAIR ? score_kernel<MODE> : (NB == 2 ? score_wide_kernel<MODE> : score_pair_kernel<MODE>);
+  static bool attr_set = false;                               // one flag per <MODE, PAIR, NB> instantiation
+  if (!attr_set) {
+    XMVE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
   }
-  return launch_status(PAIR ? "score_pair_kernel" : "score_kernel");
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tm_a, tm_b, p);
+  return launch_status(!PAIR ? "score_kernel" : (NB == 2 ? "score_wide_kernel" : "score_pair_kernel"));
 }
 
+// Tile choice (measured, profiles/r1_tile_schedule_sweep.md).  When both operands fit in L2 the wide tile is the
+// fastest (it moves the fewest operand bytes per flop; the kernel runs at the 1 kW power cap, so bytes are
+// clocks).  When the corpus streams from HBM the CTA-pair kernels re-fetch corpus lines ~10x (72 % L2 hit rate,
+// 90-150 GB of DRAM reads for an 8.2 GB operand; cause not yet understood -- same schedule, same placement
+// under a cluster launch, L2 hints and k-rotation make no difference) while the single-CTA tile reads every
+// corpus line once (95 % hits) and sustains ~10 % more flop/s, so it is the choice for large corpora.
 template <int MODE>
 int launch(const void* a_op, int64_t nq, int64_t a_ld, const void* b_op, int64_t nv, int64_t b_ld, int64_t b_row_step,
            int k, Params p, cudaStream_t stream) {
-  bool pair = true;
-  if (const char* env = getenv("XMVE_CTA_PAIR")) pair = atoi(env) != 0;
-  if (pair) return launch_cfg<MODE, true>(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k, p, stream);
-  return launch_cfg<MODE, false>(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k, p, stream);
+  const int64_t operand_bytes = (nq + nv) * static_cast<int64_t>(k) * 2;
+  int tile = operand_bytes <= (int64_t(48) << 20) ? (k >= 512 ? 2 : 1) : 0;
+  if (const char* env = getenv("XMVE_TILE")) tile = atoi(env);
+  if (tile == 2) return launch_cfg<MODE, true, 2>(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k, p, stream);
+  if (tile == 1) return launch_cfg<MODE, true, 1>(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k, p, stream);
+  return launch_cfg<MODE, false, 1>(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k, p, stream);
 }
 
 }  // namespace

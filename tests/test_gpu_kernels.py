@@ -68,8 +68,10 @@ def test_prepare_rows(N, n, d, frames, dtype):
 SHAPES = [(1000, 1000, 1536), (77, 333, 100), (128, 256, 64), (129, 257, 192), (60, 70000, 2048), (513, 5000, 640)]
 
 
+@pytest.mark.parametrize("tile", [2, 1, 0])      # wide pair tile 256x512 / pair tile 256x256 / single-CTA 128x256
 @pytest.mark.parametrize("nq,nv,d", SHAPES)
-def test_score_store_matches_fp32_matmul_of_the_operands(N, nq, nv, d):
+def test_score_store_matches_fp32_matmul_of_the_operands(N, nq, nv, d, tile, monkeypatch):
+    monkeypatch.setenv("XMVE_TILE", str(tile))
     q, v, a, b = _operands(N, nq, nv, d, seed=nq + nv)
     out = torch.full((nq, nv), float("nan"), dtype=torch.float32, device="cuda")
     N.call("xmve_score_store", N.ptr(a), nq, a.stride(0), N.ptr(b), nv, b.stride(0), 1, a.shape[1], -1.0, N.ptr(out), nv,
@@ -103,8 +105,10 @@ def test_score_store_strided_sample(N):
     assert (out.double() - ref).abs().max().item() < 2e-6
 
 
+@pytest.mark.parametrize("tile", [2, 1, 0])
 @pytest.mark.parametrize("nq,nv,d,use_hi", [(300, 50000, 512, False), (77, 3000, 100, True), (1000, 200000, 128, False)])
-def test_score_filter_window(N, nq, nv, d, use_hi):
+def test_score_filter_window(N, nq, nv, d, use_hi, tile, monkeypatch):
+    monkeypatch.setenv("XMVE_TILE", str(tile))
     q, v, a, b = _operands(N, nq, nv, d, seed=11)
     s = (a[:nq].float() @ b[:nv].float().T)
     lo = torch.quantile(s[:, :2000], 0.98, dim=1).contiguous()

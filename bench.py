@@ -26,6 +26,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -133,22 +134,48 @@ def run_reference_arm(args):
 # B200 arm
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML on a thread every 5 ms
+    (nvidia-smi -lms 200 as a fallback when pynvml is missing)."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self.stop_flag, self.thread, self.p, self.f = False, None, None, None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
-                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+            def loop():
+                while not self.stop_flag:
+                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for name, bit in bits.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                    time.sleep(0.005)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.thread = None
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                           "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                          stderr=subprocess.DEVNULL)
+            except OSError:
+                self.p = None
+
+    def _stop_smi(self):
         if self.p is None:
-            return out
+            return
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -156,28 +183,35 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        clocks, mx, reasons = [], None, set()
         for ln in self.f.read().splitlines():
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 6:
                 continue
             try:
-                clocks.append(float(parts[0]))
-                mx = float(parts[1])
+                self.samples.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
             except ValueError:
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
                 if val.lower().startswith("active"):
-                    reasons.add(name)
+                    self.reasons.add(name)
         self.f.close()
         os.unlink(self.f.name)
-        if clocks:
-            clocks.sort()
-            out["sm_mhz"] = clocks[len(clocks) // 2]
-            out["sm_max_mhz"] = mx
-        out["reasons"] = sorted(reasons)
-        out["samples"] = len(clocks)
-        out["sm_mhz_min_max"] = [clocks[0], clocks[-1]] if clocks else None
+
+    def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join()
+        else:
+            self._stop_smi()
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.samples:
+            c = sorted(self.samples)
+            out["sm_mhz"] = c[len(c) // 2]
+            out["sm_mhz_min_max"] = [c[0], c[-1]]
+        if self.power:
+            pw = sorted(self.power)
+            out["power_w"] = pw[len(pw) // 2]
         return out
 
 

@@ -277,10 +277,10 @@ def run_b200_arm(args):
     engine.N.call = timed_call
 
     def step_device():
-        return distributed.sharded_search(store, q_dev, k, weights=WEIGHTS)
+        return distributed.sharded_search(store, q_dev, k, weights=WEIGHTS, n_total=args.nv)
 
     def step_e2e():
-        s, i = distributed.sharded_search(store, q_host, k, weights=WEIGHTS)
+        s, i = distributed.sharded_search(store, q_host, k, weights=WEIGHTS, n_total=args.nv)
         out_s_host.copy_(s, non_blocking=True)
         out_i_host.copy_(i, non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -49,7 +49,7 @@ template <typename T>
 __global__ void __launch_bounds__(WARPS * 32)
 prepare_rows_kernel(const T* __restrict__ src, int64_t n, int d, int frames, int64_t src_ld,
                     float* __restrict__ raw_out, int64_t raw_ld, int64_t raw_off, double* __restrict__ norm_out,
-                    __nv_bfloat16* __restrict__ op_out, int64_t op_ld, int64_t op_off, int layout, int dpad,
+                    float* __restrict__ resid_out, __nv_bfloat16* __restrict__ op_out, int64_t op_ld, int64_t op_off, int layout, int dpad,
                     float weight, int norm_mode, int vec4) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS + (threadIdx.x >> 5);
@@ -81,10 +81,18 @@ prepare_rows_kernel(const T* __restrict__ src, int64_t n, int d, int frames, int
   const double den = (norm_mode == XMVE_NORM_EPS) ? fmax(nrm, 1e-12) : nrm;
   __nv_bfloat16* __restrict__ op = op_out + row * op_ld + op_off;
   const int planes = (layout == XMVE_OP_X1) ? 1 : 3;
+  double rs = 0.0;                           // || w * x_hat - bf16(w * x_hat) ||^2 of this row (x1 operand)
   for (int i = lane; i < d; i += 32) {
     const float x = pooled(r, i, d, frames);
-    const float xhat = static_cast<float>(static_cast<double>(x) / den);
-    write_planes(op, i, dpad, layout, weight * xhat);
+    const double xd = static_cast<double>(x) / den;
+    const float y = weight * static_cast<float>(xd);
+    write_planes(op, i, dpad, layout, y);
+    const double delta = static_cast<double>(weight) * xd - static_cast<double>(__bfloat162float(__float2bfloat16_rn(y)));
+    rs += delta * delta;
+  }
+  if (resid_out != nullptr) {
+    rs = warp_sum(rs);
+    if (lane == 0) resid_out[row] = __double2float_ru(rs);
   }
   for (int pl = 0; pl < planes; ++pl)
     for (int i = d + lane; i < dpad; i += 32) op[pl * dpad + i] = __float2bfloat16_rn(0.f);
@@ -114,9 +122,9 @@ normalize_f64_kernel(const T* __restrict__ src, int64_t n, int d, int64_t src_ld
 }  // namespace xmve
 
 extern "C" int xmve_prepare_rows(const void* src, int src_dtype, int64_t n, int d, int frames, int64_t src_ld,
-                                 float* raw_out, int64_t raw_ld, int64_t raw_off, double* norm_out, void* op_out,
-                                 int64_t op_ld, int64_t op_off, int op_layout, float weight, int norm_mode,
-                                 void* stream) {
+                                 float* raw_out, int64_t raw_ld, int64_t raw_off, double* norm_out, float* resid_out,
+                                 void* op_out, int64_t op_ld, int64_t op_off, int op_layout, float weight,
+                                 int norm_mode, void* stream) {
   using namespace xmve;
   XMVE_DEVICE_OR_RETURN();
   XMVE_REQUIRE(src != nullptr && n >= 0 && d > 0 && frames >= 1, "prepare_rows: bad src / n / d / frames");
@@ -128,6 +136,7 @@ extern "C" int xmve_prepare_rows(const void* src, int src_dtype, int64_t n, int 
   XMVE_REQUIRE(op_out == nullptr || op_ld >= op_off + static_cast<int64_t>(planes) * dpad,
                "prepare_rows: operand row too short for %d plane(s) of %d", planes, dpad);
   XMVE_REQUIRE(raw_out == nullptr || raw_ld >= raw_off + d, "prepare_rows: raw row too short");
+  XMVE_REQUIRE(resid_out == nullptr || op_out != nullptr, "prepare_rows: resid_out needs op_out");
   if (n == 0) return XMVE_OK;
   const unsigned grid = static_cast<unsigned>((n + WARPS - 1) / WARPS);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -137,12 +146,12 @@ extern "C" int xmve_prepare_rows(const void* src, int src_dtype, int64_t n, int 
                       (raw_out == nullptr || (raw_ld % 4 == 0 && raw_off % 4 == 0 && aligned16(raw_out))))
                          ? 1 : 0;
     prepare_rows_kernel<float><<<grid, WARPS * 32, 0, st>>>(static_cast<const float*>(src), n, d, frames, src_ld,
-                                                            raw_out, raw_ld, raw_off, norm_out, op, op_ld, op_off,
-                                                            op_layout, dpad, weight, norm_mode, vec4);
+                                                            raw_out, raw_ld, raw_off, norm_out, resid_out, op, op_ld,
+                                                            op_off, op_layout, dpad, weight, norm_mode, vec4);
   } else {
     prepare_rows_kernel<double><<<grid, WARPS * 32, 0, st>>>(static_cast<const double*>(src), n, d, frames, src_ld,
-                                                             raw_out, raw_ld, raw_off, norm_out, op, op_ld, op_off,
-                                                             op_layout, dpad, weight, norm_mode, 0);
+                                                             raw_out, raw_ld, raw_off, norm_out, resid_out, op, op_ld,
+                                                             op_off, op_layout, dpad, weight, norm_mode, 0);
   }
   return launch_status("prepare_rows_kernel");
 }

@@ -66,6 +66,50 @@ row_kth_kernel(const float* __restrict__ vals, int64_t cols, int64_t ld, const i
   if (threadIdx.x == 0) out[r] = res;
 }
 
+// The J largest values of each row, descending, -inf padded.  Used to combine order statistics across corpus
+// shards: the j-th largest of a union is among the per-shard top-j lists.
+__global__ void __launch_bounds__(256)
+row_topj_kernel(const float* __restrict__ vals, int64_t cols, int64_t ld, const int32_t* __restrict__ counts, int J,
+                int P, float* __restrict__ out) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t bcast[2];
+  __shared__ int n_buf;
+  extern __shared__ float topj_buf[];
+  const int64_t r = blockIdx.x;
+  int64_t n = cols;
+  if (counts != nullptr) n = min(static_cast<int64_t>(counts[r]), cols);
+  const float* row = vals + r * ld;
+  if (threadIdx.x == 0) n_buf = 0;
+  const float t = block_kth_largest(row, n, J, hist, bcast);       // -inf when the row has fewer than J values
+  __syncthreads();
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = row[i];
+    if (v > t) topj_buf[atomicAdd(&n_buf, 1)] = v;                  // strictly above the J-th largest: < J values
+  }
+  __syncthreads();
+  const int c = n_buf;
+  const int have = static_cast<int>(min(static_cast<int64_t>(J), n));
+  for (int i = c + threadIdx.x; i < P; i += blockDim.x) topj_buf[i] = (i < have) ? t : -CUDART_INF_F;
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int x = threadIdx.x; x < P; x += blockDim.x) {
+        const int o = x ^ stride;
+        if (o > x) {
+          const bool desc = (x & size) == 0;
+          const float a = topj_buf[x], b = topj_buf[o];
+          if (desc ? (b > a) : (a > b)) {
+            topj_buf[x] = b;
+            topj_buf[o] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < J; i += blockDim.x) out[r * J + i] = topj_buf[i];
+}
+
 // ---- bitonic top-k ------------------------------------------------------------------------------
 template <typename IdxT>
 __device__ __forceinline__ bool before(double sa, IdxT ia, double sb, IdxT ib) {
@@ -87,8 +131,8 @@ template <typename IdxT>
 __global__ void __launch_bounds__(512)
 select_topk_kernel(const double* __restrict__ score, const IdxT* __restrict__ idx, int64_t cols,
                    const int32_t* __restrict__ counts, int64_t idx_offset, const int64_t* __restrict__ exclude, int k,
-                   const float* __restrict__ thr, float eps, const float* __restrict__ bound, int pmax,
-                   double* __restrict__ out_score, int64_t* __restrict__ out_idx, int32_t* __restrict__ out_valid,
+                   const float* __restrict__ thr, float eps, const float* __restrict__ bound,
+                   const int32_t* __restrict__ overflow, int pmax, double* __restrict__ out_score, int64_t* __restrict__ out_idx, int32_t* __restrict__ out_valid,
                    int32_t* __restrict__ cert, float* __restrict__ thr_next) {
   extern __shared__ __align__(16) uint8_t sel_smem[];
   double* keys = reinterpret_cast<double*>(sel_smem);
@@ -101,6 +145,7 @@ select_topk_kernel(const double* __restrict__ score, const IdxT* __restrict__ id
     cand_overflow = counts[r] > cols;
     n_in = min(static_cast<int64_t>(counts[r]), cols);
   }
+  if (overflow != nullptr && overflow[r] != 0) cand_overflow = true;   // a shard's candidate list overflowed
   if (threadIdx.x == 0) n_valid_s = 0;
   __syncthreads();
   const int64_t excl = exclude ? exclude[r] : -1;
@@ -176,8 +221,8 @@ int pow2_ceil(int64_t x) {
 template <typename IdxT>
 int launch_select(const double* score, const IdxT* idx, int64_t rows, int64_t cols, const int32_t* counts,
                   int64_t idx_offset, const int64_t* exclude, int32_t k, const float* thr, float eps,
-                  const float* bound, double* out_score, int64_t* out_idx, int32_t* out_valid, int32_t* cert,
-                  float* thr_next, cudaStream_t st) {
+                  const float* bound, const int32_t* overflow, double* out_score, int64_t* out_idx, int32_t* out_valid,
+                  int32_t* cert, float* thr_next, cudaStream_t st) {
   XMVE_REQUIRE(score && out_score && out_idx && rows >= 0 && cols > 0 && k > 0, "select_topk: bad arguments");
   XMVE_REQUIRE(cert == nullptr || thr != nullptr, "select_topk: cert needs thr");
   if (rows == 0) return XMVE_OK;
@@ -197,8 +242,8 @@ int launch_select(const double* score, const IdxT* idx, int64_t rows, int64_t co
     attr_bytes[which] = smem_bytes;
   }
   select_topk_kernel<IdxT><<<static_cast<unsigned>(rows), 512, smem_bytes, st>>>(
-      score, idx, cols, counts, idx_offset, exclude, k, thr, eps, bound, pmax, out_score, out_idx, out_valid, cert,
-      thr_next);
+      score, idx, cols, counts, idx_offset, exclude, k, thr, eps, bound, overflow, pmax, out_score, out_idx, out_valid,
+      cert, thr_next);
   return launch_status("select_topk_kernel");
 }
 
@@ -223,15 +268,29 @@ extern "C" int xmve_select_topk_i32(const double* score, const int32_t* idx, int
                                     void* stream) {
   using namespace xmve;
   XMVE_DEVICE_OR_RETURN();
-  return launch_select<int32_t>(score, idx, rows, cols, counts, idx_offset, exclude, k, thr, eps, bound, out_score,
-                                out_idx, out_valid, cert, thr_next, static_cast<cudaStream_t>(stream));
+  return launch_select<int32_t>(score, idx, rows, cols, counts, idx_offset, exclude, k, thr, eps, bound, nullptr,
+                                out_score, out_idx, out_valid, cert, thr_next, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int xmve_select_topk_i64(const double* score, const int64_t* idx, int64_t rows, int64_t cols,
-                                    const int64_t* exclude, int32_t k, double* out_score, int64_t* out_idx,
-                                    int32_t* out_valid, void* stream) {
+                                    const int64_t* exclude, int32_t k, const float* thr, float eps,
+                                    const int32_t* overflow, double* out_score, int64_t* out_idx, int32_t* out_valid,
+                                    int32_t* cert, float* thr_next, void* stream) {
   using namespace xmve;
   XMVE_DEVICE_OR_RETURN();
-  return launch_select<int64_t>(score, idx, rows, cols, nullptr, 0, exclude, k, nullptr, 0.f, nullptr, out_score,
-                                out_idx, out_valid, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+  return launch_select<int64_t>(score, idx, rows, cols, nullptr, 0, exclude, k, thr, eps, nullptr, overflow, out_score,
+                                out_idx, out_valid, cert, thr_next, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int xmve_row_topj(const float* vals, int64_t rows, int64_t cols, int64_t ld, const int32_t* counts,
+                             int32_t j, float* out, void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  XMVE_REQUIRE(vals && out && rows >= 0 && cols > 0 && ld >= cols && j > 0, "row_topj: bad arguments");
+  if (j > 4096) return fail(XMVE_ERR_LIMIT, "row_topj: j=%d exceeds 4096", j);
+  if (rows == 0) return XMVE_OK;
+  const int P = pow2_ceil(j);
+  row_topj_kernel<<<static_cast<unsigned>(rows), 256, P * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      vals, cols, ld, counts, j, P, out);
+  return launch_status("row_topj_kernel");
 }

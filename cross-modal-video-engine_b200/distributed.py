@@ -1,9 +1,12 @@
 """Corpus sharding across GPUs: one process per GPU, contiguous row ranges, replicated queries.
 
-Every rank searches its own shard (local exact top-k with global row numbers); one ``all_gather`` of the
-``[nq, k]`` (score, index) blocks over NCCL / NVLink and a G-way merge kernel (K3) give every rank the
-global top-k.  Exact fp64 scores are comparable across shards, so the merge is exact.  The reference has
-no multi-GPU path for this stage; this is the design of section 8e.
+Every rank runs the search pipeline on its own shard against ONE global per-query threshold
+(``engine.search_shards``): two small ``all_gather`` s of per-shard order statistics (the top-J sample scores,
+then the top-k approximate candidate scores; ~2-3 MB per rank at 8192 queries) make every shard append and
+rescore only its share of the candidates, and one ``all_gather`` of the ``[nq, k]`` exact (score, index) lists
+over NCCL / NVLink followed by the G-way merge kernel (K3) gives every rank the certified global top-k.  Exact
+fp64 scores are comparable across shards, so the merge is exact.  The reference has no multi-GPU path for this
+stage; this is the design of section 8e.
 """
 from __future__ import annotations
 
@@ -16,6 +19,30 @@ def shard_range(n_total, world_size, rank):
     base, rem = divmod(int(n_total), int(world_size))
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+class GroupComm:
+    """The collectives ``engine.search_shards`` needs, over a ``torch.distributed`` group (nccl or gloo)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+
+    def gather(self, t):
+        """``t`` (same shape on every rank) -> ``[world, *t.shape]`` on every rank."""
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(parts, t.contiguous(), group=self.group)
+        return torch.stack(parts)
+
+    def max_(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def sum_int(self, v):
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        t = torch.tensor([int(v)], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return int(t.item())
 
 
 def gather_topk(scores, idx, group=None):
@@ -42,11 +69,11 @@ def merge_reference(scores, idx, k):
     return torch.gather(s, 1, order)[:, :k], torch.gather(i, 1, order)[:, :k]
 
 
-def sharded_search(store, queries, k, group=None, **kw):
-    """Search this rank's shard, all-gather, merge on the device.  Returns global ``(scores, idx)``."""
-    from .engine import merge_topk
-    s, i = store.search(queries, k, **kw)
+def sharded_search(store, queries, k, group=None, n_total=None, **kw):
+    """Search the corpus whose rows are sharded over the ranks of ``group``; every rank passes the same queries
+    and gets the same global ``(scores, idx)``.  ``n_total`` (the global row count) saves one tiny all-reduce."""
+    from .engine import search_shards
+    stores = list(store) if isinstance(store, (list, tuple)) else [store]
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return s, i
-    s_all, i_all = gather_topk(s, i, group)
-    return merge_topk(s_all, i_all, k)
+        return search_shards(stores, queries, k, **kw)
+    return search_shards(stores, queries, k, comm=GroupComm(group), n_total=n_total, **kw)

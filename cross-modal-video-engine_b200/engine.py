@@ -30,9 +30,11 @@ import torch
 
 from . import _native as N
 
-#: worst-case |bf16-operand score - exact cosine| for unit vectors: 2 * 2^-9 relative per product
-#: (Cauchy-Schwarz) plus fp32 accumulation slack.
-EPS_X1 = 4.5e-3
+#: a-priori bound on |bf16-operand score - exact cosine| per unit of fusion weight: bf16 keeps 8 significant bits,
+#: so rounding moves a vector by at most 2^-8 of its norm and a product of two unit vectors by at most 2 * 2^-8
+#: (Cauchy-Schwarz); plus fp32 accumulation slack.  Used only when no measured residuals are available
+#: (search(eps=...) callers, NaN rows); the search itself uses :func:`measured_eps` (typically 3.5e-3 - 4e-3).
+EPS_X1 = 8.5e-3
 SMALL_NV = 16384
 _BM, _BN = 128, 256
 
@@ -66,7 +68,7 @@ def _to_device(x, device):
     return x
 
 
-def _prepare(src, d, raw, raw_off, norm, op, op_off, layout, weight, norm_mode):
+def _prepare(src, d, raw, raw_off, norm, resid, op, op_off, layout, weight, norm_mode):
     """One K1 launch for one embedding space of one batch of rows."""
     frames = 1
     if src.dim() == 3:
@@ -81,7 +83,7 @@ def _prepare(src, d, raw, raw_off, norm, op, op_off, layout, weight, norm_mode):
     N.call("xmve_prepare_rows", N.ptr(src), N.F64 if src.dtype == torch.float64 else N.F32, n, d, frames,
            src.stride(0),
            N.ptr(raw), raw.stride(0) if raw is not None else 0, raw_off,
-           N.ptr(norm),
+           N.ptr(norm), N.ptr(resid),
            N.ptr(op), op.stride(0) if op is not None else 0, op_off, layout,
            float(weight), norm_mode, N.stream_ptr())
 
@@ -111,6 +113,8 @@ class CorpusStore:
         self.op = torch.zeros((rows, self.k), dtype=torch.bfloat16, device=self.device)
         self.raw = torch.empty((max(self.capacity, 1), self.raw_ld), dtype=torch.float32, device=self.device)
         self.norm = torch.empty((len(self.dims), max(self.capacity, 1)), dtype=torch.float64, device=self.device)
+        self.resid = torch.zeros((len(self.dims), max(self.capacity, 1)), dtype=torch.float32, device=self.device)
+        self._resid_max2 = None
         self.space_off = (C.c_int32 * (len(self.dims) + 1))(*([0] + list(_cumsum(self.dims))))
 
     # -- ingest ----------------------------------------------------------------------------------
@@ -123,8 +127,8 @@ class CorpusStore:
         op_off = raw_off = 0
         for s, (src, d, dp) in enumerate(zip(spaces, self.dims, self.dpads)):
             assert src.shape[-1] == d, "space %d: expected dim %d, got %d" % (s, d, src.shape[-1])
-            _prepare(src, d, self.raw[self.n:], raw_off, self.norm[s, self.n:], self.op[self.n:], op_off,
-                     N.OP_X1, 1.0, self.norm_mode)
+            _prepare(src, d, self.raw[self.n:], raw_off, self.norm[s, self.n:], self.resid[s, self.n:],
+                     self.op[self.n:], op_off, N.OP_X1, 1.0, self.norm_mode)
             op_off += dp
             raw_off += d
         self.n += n
@@ -132,55 +136,49 @@ class CorpusStore:
 
     # -- query side ------------------------------------------------------------------------------
     def prepare_queries(self, queries, weights=None):
-        """K1 on the query batch: returns (a_op bf16 [nq_pad, K], q_raw fp32 [nq, raw_ld], q_norm fp64 [S, nq])."""
+        """K1 on the query batch: returns (a_op bf16 [nq_pad, K], q_raw fp32 [nq, raw_ld], q_norm fp64 [S, nq],
+        q_resid fp32 [S, nq] squared bf16 residuals, nq)."""
         weights = _weights(weights, len(self.dims))
         spaces = [_to_device(s, self.device) for s in _as_spaces(queries, self.dims)]
         nq = spaces[0].shape[0]
         a_op = torch.zeros((_round_up(max(nq, 1), _BM), self.k), dtype=torch.bfloat16, device=self.device)
         q_raw = torch.empty((max(nq, 1), self.raw_ld), dtype=torch.float32, device=self.device)
         q_norm = torch.empty((len(self.dims), max(nq, 1)), dtype=torch.float64, device=self.device)
+        q_res = torch.zeros((len(self.dims), max(nq, 1)), dtype=torch.float32, device=self.device)
         op_off = raw_off = 0
         for s, (src, d, dp) in enumerate(zip(spaces, self.dims, self.dpads)):
-            _prepare(src, d, q_raw, raw_off, q_norm[s], a_op, op_off, N.OP_X1, weights[s], self.norm_mode)
+            _prepare(src, d, q_raw, raw_off, q_norm[s], q_res[s], a_op, op_off, N.OP_X1, weights[s], self.norm_mode)
             op_off += dp
             raw_off += d
-        return a_op, q_raw, q_norm, nq
+        return a_op, q_raw, q_norm, q_res, nq
 
     # -- search ----------------------------------------------------------------------------------
-    def search(self, queries, k, weights=None, exclude=None, eps=EPS_X1, small_nv=SMALL_NV, stats=None):
+    def search(self, queries, k, weights=None, exclude=None, eps=None, small_nv=SMALL_NV, stats=None):
         """Top-``k`` corpus rows per query by fused cosine score, exact (fp64) scores, descending.
 
         Returns ``(scores float64 [nq, k], idx int64 [nq, k])`` on the device; ``idx`` are global row
-        numbers (``index_offset`` + local), ``-1`` / ``-inf`` padded if the shard has fewer than ``k``
+        numbers (``index_offset`` + local), ``-1`` / ``-inf`` padded if the corpus has fewer than ``k``
         rows.  ``exclude[q]`` (global row or -1) is dropped from row q's list -- MultiFusion's removal
-        of the query's own reference item (validate.py:76-83).
+        of the query's own reference item (validate.py:76-83).  ``eps`` overrides the measured bound on
+        |tensor-core score - exact score| (see :func:`measured_eps`).
         """
-        if self.n == 0:
-            raise ValueError("empty corpus")
-        wts = _weights(weights, len(self.dims))
-        eps = float(eps) * max(1.0, sum(abs(w) for w in wts))      # the error bound scales with sum |w_s|
-        a_op, q_raw, q_norm, nq = self.prepare_queries(queries, wts)
-        if nq == 0:
-            return (torch.empty((0, k), dtype=torch.float64, device=self.device),
-                    torch.empty((0, k), dtype=torch.int64, device=self.device))
-        excl = None
-        if exclude is not None:
-            excl = torch.as_tensor(exclude, dtype=torch.int64).to(self.device)
-        k_eff = min(int(k), self.n)
-        out_s = torch.full((nq, k), float("-inf"), dtype=torch.float64, device=self.device)
-        out_i = torch.full((nq, k), -1, dtype=torch.int64, device=self.device)
-        if self.n <= small_nv:
-            s_, i_ = self._search_exact_small(q_raw, q_norm, nq, k_eff, wts, excl)
-        else:
-            s_, i_ = self._search_filtered(a_op, q_raw, q_norm, nq, k_eff, wts, excl, eps, stats)
-        out_s[:, :k_eff] = s_
-        out_i[:, :k_eff] = i_
-        return out_s, out_i
+        return search_shards([self], queries, k, weights=weights, exclude=exclude, eps=eps, small_nv=small_nv,
+                             stats=stats)
+
+    def plan(self, k, n=None):
+        return plan(k, self.n if n is None else n)
+
+    def resid_max2(self):
+        """max over rows of the squared bf16 quantisation residual of the operand (device scalar, cached)."""
+        if self._resid_max2 is None or self._resid_max2[0] != self.n:
+            r = self.resid[:, :self.n].sum(0).max() if self.n else torch.zeros((), device=self.device)
+            self._resid_max2 = (self.n, r)
+        return self._resid_max2[1]
 
     def _weights_arr(self, wts):
         return (C.c_double * len(wts))(*[float(w) for w in wts])
 
-    def _search_exact_small(self, q_raw, q_norm, nq, k, wts, excl):
+    def _exact_small(self, q_raw, q_norm, nq, k, wts, excl):
         """fp64 score matrix + bitonic top-k (corpora up to ``small_nv`` rows)."""
         dev, st = self.device, N.stream_ptr()
         acc = None
@@ -199,108 +197,294 @@ class CorpusStore:
                        N.ptr(sc[q0:]), self.n, st)
             acc = sc if acc is None else acc.add_(sc)
             o += d
-        out_s = torch.empty((nq, k), dtype=torch.float64, device=dev)
-        out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        N.call("xmve_select_topk_i32", N.ptr(acc), None, nq, self.n, None, self.index_offset, N.ptr(excl), k,
-               None, 0.0, None, N.ptr(out_s), N.ptr(out_i), None, None, None, st)
+        kk = min(k, self.n)
+        out_s = torch.full((nq, k), float("-inf"), dtype=torch.float64, device=dev)
+        out_i = torch.full((nq, k), -1, dtype=torch.int64, device=dev)
+        s_ = torch.empty((nq, kk), dtype=torch.float64, device=dev)
+        i_ = torch.empty((nq, kk), dtype=torch.int64, device=dev)
+        N.call("xmve_select_topk_i32", N.ptr(acc), None, nq, self.n, None, self.index_offset, N.ptr(excl), kk,
+               None, 0.0, None, N.ptr(s_), N.ptr(i_), None, None, None, st)
+        out_s[:, :kk] = s_
+        out_i[:, :kk] = i_
         return out_s, out_i
 
-    def plan(self, k, n=None):
-        """Sampling step, order statistics and candidate capacity for a top-``k`` search of ``n`` rows."""
-        n = self.n if n is None else int(n)
-        n_s = min(n, max(8192, min(65536, n // 128)))
-        step = max(1, n // max(n_s, 1))
-        n_s = (n + step - 1) // step
-        lam = k / step
-        j = int(math.ceil(lam + 5.5 * math.sqrt(lam) + 4))
-        cap = 1 << max(11, int(math.ceil(math.log2(8 * step * j))))
-        cap = min(cap, 32768)
-        j_cap = max(j, int(0.5 * cap / step))
-        return {"step": step, "n_sample": n_s, "j": min(j, n_s), "j_cap": min(j_cap, n_s), "cap": cap}
+    # one shard's share of a filtered pass ----------------------------------------------------------
+    def _sample(self, a_op, nq, step):
+        """K2 STORE over every ``step``-th row of this shard -> fp32 ``[nq, ceil(n / step)]``."""
+        n_s = (self.n + step - 1) // step
+        sample = torch.empty((nq, n_s), dtype=torch.float32, device=self.device)
+        N.call("xmve_score_store", N.ptr(a_op), nq, a_op.stride(0), N.ptr(self.op), n_s, self.op.stride(0), step,
+               self.k, 1.0, N.ptr(sample), sample.stride(0), N.stream_ptr())
+        return sample
 
-    def _search_filtered(self, a_op, q_raw, q_norm, nq, k, wts, excl, eps, stats):
-        dev, st = self.device, N.stream_ptr()
-        kk = k + (1 if excl is not None else 0)           # one extra in case the excluded row is among them
-        pl = self.plan(kk)
-        # 2-3: sampled threshold  thr = max(kth(sample, j) - 2 eps, kth(sample, j_cap))
-        sample = torch.empty((nq, pl["n_sample"]), dtype=torch.float32, device=dev)
-        N.call("xmve_score_store", N.ptr(a_op), nq, a_op.stride(0), N.ptr(self.op), pl["n_sample"],
-               self.op.stride(0), pl["step"], self.k, 1.0, N.ptr(sample), sample.stride(0), st)
-        thr = torch.empty((nq,), dtype=torch.float32, device=dev)
-        N.call("xmve_row_kth", N.ptr(sample), nq, pl["n_sample"], sample.stride(0), None, pl["j"], 2.0 * eps,
-               pl["j_cap"], N.ptr(thr), st)
-        del sample
-        out_s = torch.empty((nq, k), dtype=torch.float64, device=dev)
-        out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        rows = None                                        # None = all rows; else LongTensor of rows to re-run
-        cap = pl["cap"]
-        for attempt in range(12):
-            if rows is None:
-                a_sub, q_sub, qn_sub, thr_sub, ex_sub, n_sub = a_op, q_raw, q_norm, thr, excl, nq
-            else:
-                n_sub = rows.numel()
-                a_sub = torch.zeros((_round_up(n_sub, _BM), self.k), dtype=torch.bfloat16, device=dev)
-                a_sub[:n_sub] = a_op[rows]
-                q_sub = q_raw[rows].contiguous()
-                qn_sub = q_norm[:, rows].contiguous()
-                thr_sub = thr[rows].contiguous()
-                ex_sub = excl[rows].contiguous() if excl is not None else None
-            s_, i_, cert, thr_next, cnt = self._filter_pass(a_sub, q_sub, qn_sub, n_sub, k, kk, wts, ex_sub, thr_sub,
-                                                            eps, cap)
-            bad = torch.nonzero(cert == 0).flatten()       # device -> host sync (the step's only one)
-            if rows is None:
-                out_s, out_i = s_, i_
-            else:
-                out_s[rows] = s_
-                out_i[rows] = i_
-            if bad.numel() == 0:
-                break
-            # an overflowed row needs a HIGHER threshold; if the kernel cannot propose one, grow the lists
-            stuck = (cnt[bad] > cap) & (thr_next[bad] <= thr_sub[bad])
-            if rows is None:
-                thr = thr.clone()
-                thr[bad] = thr_next[bad]
-                rows = bad
-            else:
-                thr[rows[bad]] = thr_next[bad]
-                rows = rows[bad]
-            if stats is not None:
-                stats["reruns"] = stats.get("reruns", 0) + 1
-                stats["rerun_rows"] = stats.get("rerun_rows", 0) + int(rows.numel())
-            if bool(stuck.any()) and cap < 32768:
-                cap = min(32768, cap * 4)                  # overflow that a tighter threshold cannot fix
-        else:
-            raise N.XmveError("search: %d row(s) could not be certified after 12 passes (increase eps headroom "
-                              "or candidate capacity; heavy score ties?)" % int(rows.numel()))
-        return out_s, out_i
-
-    def _filter_pass(self, a_op, q_raw, q_norm, nq, k, kk, wts, excl, thr, eps, cap):
-        dev, st = self.device, N.stream_ptr()
+    def _filter(self, a_op, nq, thr, cap):
+        """K2 FILTER over the shard: candidates (approximate score, local row) above ``thr`` per query."""
+        dev = self.device
         cand_count = torch.zeros((nq,), dtype=torch.int32, device=dev)
         cand_score = torch.empty((nq, cap), dtype=torch.float32, device=dev)
         cand_idx = torch.empty((nq, cap), dtype=torch.int32, device=dev)
-        # 4: fused score + threshold filter; the score matrix never reaches HBM
         N.call("xmve_score_filter", N.ptr(a_op), nq, a_op.stride(0), N.ptr(self.op), self.n, self.op.stride(0),
-               self.k, N.ptr(thr), None, None, N.ptr(cand_count), N.ptr(cand_score), N.ptr(cand_idx), cap, st)
-        # 5: bound = (kk-th largest approximate candidate score) - 2 eps: nothing below it can reach the top-k
-        bound = torch.empty((nq,), dtype=torch.float32, device=dev)
-        N.call("xmve_row_kth", N.ptr(cand_score), nq, cap, cap, N.ptr(cand_count), kk, 2.0 * eps, 0, N.ptr(bound), st)
-        # 6: exact fp64 rescore of the survivors
+               self.k, N.ptr(thr), None, None, N.ptr(cand_count), N.ptr(cand_score), N.ptr(cand_idx), cap,
+               N.stream_ptr())
+        return cand_count, cand_score, cand_idx
+
+    def _rescore_select(self, q_raw, q_norm, nq, k, wts, excl, cand, bound, thr, eps, certify):
+        """Exact fp64 rescore of the candidates above ``bound`` + local top-k (global row ids)."""
+        dev, st = self.device, N.stream_ptr()
+        cand_count, cand_score, cand_idx = cand
+        cap = cand_score.shape[1]
         exact = torch.empty((nq, cap), dtype=torch.float64, device=dev)
         N.call("xmve_rescore", N.ptr(q_raw), nq, q_raw.stride(0), N.ptr(q_norm), N.ptr(self.raw), self.n,
                self.raw.stride(0), N.ptr(self.norm), len(self.dims), self.space_off, self._weights_arr(wts),
                self.norm_mode, N.ptr(cand_score), N.ptr(cand_idx), N.ptr(cand_count), cap, N.ptr(bound),
                N.ptr(exact), st)
-        # 7: final top-k + certification
         out_s = torch.empty((nq, k), dtype=torch.float64, device=dev)
         out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        cert = torch.empty((nq,), dtype=torch.int32, device=dev)
-        thr_next = torch.empty((nq,), dtype=torch.float32, device=dev)
+        cert = thr_next = None
+        if certify:
+            cert = torch.empty((nq,), dtype=torch.int32, device=dev)
+            thr_next = torch.empty((nq,), dtype=torch.float32, device=dev)
         N.call("xmve_select_topk_i32", N.ptr(exact), N.ptr(cand_idx), nq, cap, N.ptr(cand_count),
-               self.index_offset, N.ptr(excl), k, N.ptr(thr), float(eps), N.ptr(bound), N.ptr(out_s), N.ptr(out_i),
-               None, N.ptr(cert), N.ptr(thr_next), st)
-        self.last_cand_count = cand_count
-        return out_s, out_i, cert, thr_next, cand_count
+               self.index_offset, N.ptr(excl), k, N.ptr(thr) if certify else None, float(eps),
+               N.ptr(bound) if certify else None, N.ptr(out_s), N.ptr(out_i), None, N.ptr(cert), N.ptr(thr_next), st)
+        return out_s, out_i, cert, thr_next
+
+
+def plan(k, n):
+    """Sampling step, order statistics and candidate capacity for a top-``k`` search of ``n`` corpus rows."""
+    n = int(n)
+    n_s = min(n, max(8192, min(65536, n // 128)))
+    step = max(1, n // max(n_s, 1))
+    n_s = (n + step - 1) // step
+    lam = k / step
+    j = int(math.ceil(lam + 5.5 * math.sqrt(lam) + 4))
+    cap = 1 << max(11, int(math.ceil(math.log2(8 * step * j))))
+    cap = min(cap, 32768)
+    j_cap = max(j, int(0.5 * cap / step))
+    return {"step": step, "n_sample": n_s, "j": min(j, n_s), "j_cap": min(j_cap, n_s), "cap": cap}
+
+
+def measured_eps(dq, dv, wts, n_space, k_len):
+    """Rigorous bound on |tensor-core score - exact score| from the MEASURED bf16 residuals.
+
+    With Q = concat_s(w_s q_hat_s), V = concat_s(v_hat_s) and Qb, Vb their bf16 roundings,
+    ``<Q,V> - <Qb,Vb> = <Q-Qb, V> + <Qb, V-Vb>``, so by Cauchy-Schwarz the operand rounding costs at most
+    ``dq * |V| + |Qb| * dv`` with ``dq = max_q |Q-Qb|``, ``dv = max_v |V-Vb|`` (K1 measures both), ``|V| = sqrt(S)``
+    and ``|Qb| <= sqrt(sum w^2) + dq``.  The bf16 x bf16 products are exact in fp32; accumulating ``k_len`` of them
+    in fp32 (with truncation at worst) costs at most ``k_len * 2^-22 * |Qb| * |Vb|``.  The a-priori worst case is
+    2 * 2^-8 per unit weight (``EPS_X1``); Gaussian-like rows measure ``dq, dv ~ 1.7e-3`` of the norm, i.e. about half.
+    """
+    qn = math.sqrt(sum(w * w for w in wts)) + dq
+    vn = math.sqrt(n_space) * (1.0 + 2.0 ** -8)
+    e = dq * vn + qn * dv + k_len * 2.0 ** -22 * qn * vn + 1e-6
+    if not math.isfinite(e) or e <= 0.0:                   # NaN rows (zero vectors under 'plain' normalisation)
+        return EPS_X1 * max(1.0, sum(abs(w) for w in wts))
+    return e
+
+
+class SoloComm:
+    """The collective interface of :func:`search_shards` for a single process (world size 1)."""
+    world = 1
+
+    def gather(self, t):
+        return t.unsqueeze(0)
+
+    def max_(self, t):
+        return t
+
+    def sum_int(self, v):
+        return int(v)
+
+
+def _row_topj(vals, counts, j):
+    rows, cols = vals.shape
+    out = torch.empty((rows, j), dtype=torch.float32, device=vals.device)
+    if rows:
+        N.call("xmve_row_topj", N.ptr(vals), rows, cols, vals.stride(0), N.ptr(counts), j, N.ptr(out), N.stream_ptr())
+    return out
+
+
+def _row_kth(vals, counts, j1, sub, j2):
+    rows, cols = vals.shape
+    out = torch.empty((rows,), dtype=torch.float32, device=vals.device)
+    if rows:
+        N.call("xmve_row_kth", N.ptr(vals), rows, cols, vals.stride(0), N.ptr(counts), j1, float(sub), j2, N.ptr(out),
+               N.stream_ptr())
+    return out
+
+
+def _union(parts, comm):
+    """Per-row lists from the local shards ``[nq, m]`` -> the union over all shards of all ranks ``[nq, G*L*m]``."""
+    loc = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+    if comm.world == 1:
+        return loc
+    g = comm.gather(loc.contiguous())                                   # [G, nq, L*m]
+    return g.permute(1, 0, 2).reshape(loc.shape[0], -1).contiguous()
+
+
+def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, small_nv=SMALL_NV, stats=None, comm=None,
+                  n_total=None):
+    """Exact top-``k`` over a corpus cut into shards: ``stores`` are this process's shards (normally one), ``comm``
+    joins the processes of a ``torch.distributed`` group (``distributed.GroupComm``; every rank calls this function
+    with the same queries).  All shards work against ONE per-query threshold:
+
+    1. K1 on the query batch; the measured error bound ``eps`` (max over ranks).
+    2. K2 STORE over every ``step``-th row of each shard; the top-J sample scores of every shard are gathered and
+       the global threshold is ``max(kth(union, j) - 2 eps, kth(union, j_cap))`` -- what one GPU would compute on
+       the whole corpus, so each shard appends only its share of the candidates.
+    3. K2 FILTER over each shard (the score matrix never reaches HBM).
+    4. the kk-th largest approximate candidate score over all shards - 2 eps bounds what needs an exact score.
+    5. exact fp64 rescore + local top-k per shard; ONE gather of the ``[nq, k]`` lists; merge (K3) with the
+       certificate ``kth_exact - eps >= threshold`` and no overflowed list.
+    6. rows without a certificate are re-run (by all ranks alike) with the threshold the merge proposes.
+
+    Corpora of at most ``small_nv`` rows skip 2-4: every shard forms its fp64 score matrix directly.
+    With one shard and one rank no gather happens and the certificate comes from the local selection kernel.
+    """
+    comm = comm or SoloComm()
+    ref = stores[0]
+    dev, n_space = ref.device, len(ref.dims)
+    n_shards = len(stores) * comm.world
+    solo = n_shards == 1
+    n_local = sum(s.n for s in stores)
+    if n_total is None:
+        n_total = comm.sum_int(n_local)
+    if n_total == 0:
+        raise ValueError("empty corpus")
+    wts = _weights(weights, n_space)
+    a_op, q_raw, q_norm, q_res, nq = ref.prepare_queries(queries, wts)
+    if nq == 0:
+        return (torch.empty((0, k), dtype=torch.float64, device=dev), torch.empty((0, k), dtype=torch.int64, device=dev))
+    excl = None
+    if exclude is not None:
+        excl = torch.as_tensor(exclude, dtype=torch.int64).to(dev)
+    k_eff = min(int(k), n_total)
+    out_s = torch.full((nq, k), float("-inf"), dtype=torch.float64, device=dev)
+    out_i = torch.full((nq, k), -1, dtype=torch.int64, device=dev)
+
+    if n_total <= small_nv:
+        parts = [s._exact_small(q_raw, q_norm, nq, k_eff, wts, excl) for s in stores if s.n]
+        if not parts:
+            parts = [(torch.full((nq, k_eff), float("-inf"), dtype=torch.float64, device=dev),
+                      torch.full((nq, k_eff), -1, dtype=torch.int64, device=dev))]
+        if solo:
+            s_, i_ = parts[0]
+        else:
+            s_, i_ = _merge(_union([p[0] for p in parts], comm), _union([p[1] for p in parts], comm), k_eff)
+        out_s[:, :k_eff] = s_
+        out_i[:, :k_eff] = i_
+        return out_s, out_i
+
+    if eps is None:
+        m = torch.stack([q_res.sum(0).max(), torch.stack([s.resid_max2() for s in stores]).max()]).double()
+        dq2, dv2 = comm.max_(m).tolist()                       # host sync (tiny); the bound must be a host float
+        eps = measured_eps(math.sqrt(dq2), math.sqrt(dv2), wts, n_space, ref.k) if dq2 == dq2 and dv2 == dv2 \
+            else EPS_X1 * max(1.0, sum(abs(w) for w in wts))
+    else:
+        eps = float(eps) * max(1.0, sum(abs(w) for w in wts))
+    kk = k_eff + (1 if excl is not None else 0)               # one extra in case the excluded row is among them
+    pl = plan(kk, n_total)
+    live = [s for s in stores if s.n]
+    # 2: one global threshold from the shards' samples
+    samples = [s._sample(a_op, nq, pl["step"]) for s in live]
+    if solo:
+        thr = _row_kth(samples[0], None, pl["j"], 2.0 * eps, pl["j_cap"])
+    else:
+        big_j = max(pl["j"], pl["j_cap"])
+        tops = [_row_topj(sm, None, big_j) for sm in samples]
+        if not tops:
+            tops = [torch.full((nq, big_j), float("-inf"), dtype=torch.float32, device=dev)]
+        thr = _row_kth(_union(tops, comm), None, pl["j"], 2.0 * eps, pl["j_cap"])
+    del samples
+    cap = pl["cap"] if solo else max(2048, min(pl["cap"], 1 << int(math.ceil(math.log2(4.0 * pl["cap"] / n_shards)))))
+    rows = None                                               # None = all rows; else LongTensor of rows to re-run
+    for attempt in range(12):
+        if rows is None:
+            a_sub, q_sub, qn_sub, thr_sub, ex_sub, n_sub = a_op, q_raw, q_norm, thr, excl, nq
+        else:
+            n_sub = rows.numel()
+            a_sub = torch.zeros((_round_up(n_sub, _BM), ref.k), dtype=torch.bfloat16, device=dev)
+            a_sub[:n_sub] = a_op[rows]
+            q_sub = q_raw[rows].contiguous()
+            qn_sub = q_norm[:, rows].contiguous()
+            thr_sub = thr[rows].contiguous()
+            ex_sub = excl[rows].contiguous() if excl is not None else None
+        # 3: fused score + threshold filter on every local shard
+        cands = [s._filter(a_sub, n_sub, thr_sub, cap) for s in live]
+        # 4: nothing below (kk-th largest approximate candidate score) - 2 eps can reach the top-k
+        if solo:
+            bound = _row_kth(cands[0][1], cands[0][0], kk, 2.0 * eps, 0)
+        else:
+            tops = [_row_topj(c[1], c[0], kk) for c in cands]
+            if not tops:
+                tops = [torch.full((n_sub, kk), float("-inf"), dtype=torch.float32, device=dev)]
+            bound = _row_kth(_union(tops, comm), None, kk, 2.0 * eps, 0)
+        # 5: exact rescore + selection
+        if solo:
+            s_, i_, cert, thr_next = live[0]._rescore_select(q_sub, qn_sub, n_sub, k_eff, wts, ex_sub, cands[0], bound,
+                                                             thr_sub, eps, True)
+            over = cands[0][0] > cap
+        else:
+            parts = [s._rescore_select(q_sub, qn_sub, n_sub, k_eff, wts, ex_sub, c, bound, thr_sub, eps, False)
+                     for s, c in zip(live, cands)]
+            over = torch.zeros((n_sub,), dtype=torch.int32, device=dev)
+            for c in cands:
+                over |= (c[0] > cap).int()
+            over = comm.max_(over)
+            if not parts:
+                parts = [(torch.full((n_sub, k_eff), float("-inf"), dtype=torch.float64, device=dev),
+                          torch.full((n_sub, k_eff), -1, dtype=torch.int64, device=dev), None, None)]
+            s_, i_, cert, thr_next = _merge(_union([p[0] for p in parts], comm), _union([p[1] for p in parts], comm),
+                                            k_eff, thr=thr_sub, eps=eps, overflow=over)
+            over = over != 0
+        if stats is not None and rows is None:
+            stats["eps"] = eps
+            stats["cap"] = cap
+            stats["cand_count"] = [c[0] for c in cands]
+        bad = torch.nonzero(cert == 0).flatten()              # device -> host sync (identical on every rank)
+        if rows is None:
+            out_s[:, :k_eff] = s_
+            out_i[:, :k_eff] = i_
+        else:
+            out_s[rows, :k_eff] = s_
+            out_i[rows, :k_eff] = i_
+        if bad.numel() == 0:
+            break
+        # an overflowed row needs a HIGHER threshold; if the kernel cannot propose one, grow the lists
+        stuck = over[bad] & (thr_next[bad] <= thr_sub[bad])
+        if rows is None:
+            thr = thr.clone()
+            thr[bad] = thr_next[bad]
+            rows = bad
+        else:
+            thr[rows[bad]] = thr_next[bad]
+            rows = rows[bad]
+        if stats is not None:
+            stats["reruns"] = stats.get("reruns", 0) + 1
+            stats["rerun_rows"] = stats.get("rerun_rows", 0) + int(rows.numel())
+        if bool(stuck.any()) and cap < 32768:
+            cap = min(32768, cap * 4)                         # overflow that a tighter threshold cannot fix
+    else:
+        raise N.XmveError("search: %d row(s) could not be certified after 12 passes (increase eps headroom "
+                          "or candidate capacity; heavy score ties?)" % int(rows.numel()))
+    return out_s, out_i
+
+
+def _merge(scores, idx, k, thr=None, eps=0.0, overflow=None):
+    """K3 on ``[nq, m]`` (score, global index) pairs -> top-``k`` (+ certificate when ``thr`` is given)."""
+    nq, m = scores.shape
+    out_s = torch.empty((nq, k), dtype=torch.float64, device=scores.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=scores.device)
+    cert = thr_next = None
+    if thr is not None:
+        cert = torch.empty((nq,), dtype=torch.int32, device=scores.device)
+        thr_next = torch.empty((nq,), dtype=torch.float32, device=scores.device)
+    if nq:
+        N.call("xmve_select_topk_i64", N.ptr(scores), N.ptr(idx), nq, m, None, k, N.ptr(thr), float(eps),
+               N.ptr(overflow), N.ptr(out_s), N.ptr(out_i), None, N.ptr(cert), N.ptr(thr_next), N.stream_ptr())
+    if thr is None:
+        return out_s, out_i
+    return out_s, out_i, cert, thr_next
 
 
 def _cumsum(xs):
@@ -323,9 +507,4 @@ def merge_topk(scores, idx, k):
     g, nq, kk = scores.shape
     s = scores.permute(1, 0, 2).reshape(nq, g * kk).contiguous()
     i = idx.permute(1, 0, 2).reshape(nq, g * kk).contiguous()
-    out_s = torch.empty((nq, k), dtype=torch.float64, device=s.device)
-    out_i = torch.empty((nq, k), dtype=torch.int64, device=s.device)
-    if nq:
-        N.call("xmve_select_topk_i64", N.ptr(s), N.ptr(i), nq, g * kk, None, k, N.ptr(out_s), N.ptr(out_i), None,
-               N.stream_ptr())
-    return out_s, out_i
+    return _merge(s, i, k)

@@ -84,9 +84,9 @@ def score_matrix(queries, corpus, alpha, norm_mode=N.NORM_PLAIN):
     dpad = _round_up(d, 64)
     a_op = torch.zeros((_round_up(nq, _BM), 3 * dpad), dtype=torch.bfloat16, device=q.device)
     b_op = torch.zeros((_round_up(nv, _BN), 3 * dpad), dtype=torch.bfloat16, device=q.device)
-    N.call("xmve_prepare_rows", N.ptr(q), N.F32, nq, d, 1, q.stride(0), None, 0, 0, None, N.ptr(a_op), 3 * dpad, 0,
+    N.call("xmve_prepare_rows", N.ptr(q), N.F32, nq, d, 1, q.stride(0), None, 0, 0, None, None, N.ptr(a_op), 3 * dpad, 0,
            N.OP_X3_QUERY, 1.0, norm_mode, st)
-    N.call("xmve_prepare_rows", N.ptr(v), N.F32, nv, d, 1, v.stride(0), None, 0, 0, None, N.ptr(b_op), 3 * dpad, 0,
+    N.call("xmve_prepare_rows", N.ptr(v), N.F32, nv, d, 1, v.stride(0), None, 0, 0, None, None, N.ptr(b_op), 3 * dpad, 0,
            N.OP_X3_CORPUS, 1.0, norm_mode, st)
     out = torch.empty((nq, nv), dtype=torch.float32, device=q.device)
     N.call("xmve_score_store", N.ptr(a_op), nq, 3 * dpad, N.ptr(b_op), nv, 3 * dpad, 1, 3 * dpad, float(alpha),

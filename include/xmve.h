@@ -67,13 +67,16 @@ XMVE_API int xmve_sm_count(void);
  * src       [n, frames, d] fp32/fp64 (src_dtype), row stride src_ld elements (>= frames*d)
  * raw_out   optional fp32 [n, raw_ld]: the (frame-pooled) raw row is written at column raw_off
  * norm_out  optional fp64 [n]: ||x||_2 accumulated in double
+ * resid_out optional fp32 [n]: ||w*x_hat - bf16(w*x_hat)||^2 of the row's hi plane, rounded up (the measured
+ *           bf16 quantisation residual; engine.py turns the maxima of both sides into the rigorous bound
+ *           eps on |tensor-core score - exact score| that certifies the top-k)
  * op_out    optional bf16 [n, op_ld]: operand planes per op_layout written at column op_off,
  *           plane stride dpad = round_up(d, 64); columns d..dpad of each plane are zero-filled
  * weight    folded into the operand (per-space fusion weight; 1.0 on the corpus side)
  */
 XMVE_API int xmve_prepare_rows(const void* src, int src_dtype, int64_t n, int d, int frames, int64_t src_ld,
                       float* raw_out, int64_t raw_ld, int64_t raw_off,
-                      double* norm_out,
+                      double* norm_out, float* resid_out,
                       void* op_out, int64_t op_ld, int64_t op_off, int op_layout,
                       float weight, int norm_mode, void* stream);
 
@@ -145,10 +148,18 @@ XMVE_API int xmve_select_topk_i32(const double* score, const int32_t* idx, int64
                          double* out_score, int64_t* out_idx, int32_t* out_valid,
                          int32_t* cert, float* thr_next, void* stream);
 /* K3: G-way merge of per-shard top-k lists after the all-gather: rows x (G*k) pairs with global
- * int64 indices -> top-k.  Same ordering rule. */
+ * int64 indices -> top-k.  Same ordering rule.  With thr != NULL the merged list is certified like above
+ * (cert, thr_next); overflow[r] != 0 says that some shard's candidate list of row r overflowed. */
 XMVE_API int xmve_select_topk_i64(const double* score, const int64_t* idx, int64_t rows, int64_t cols,
                          const int64_t* exclude, int32_t k,
-                         double* out_score, int64_t* out_idx, int32_t* out_valid, void* stream);
+                         const float* thr, float eps, const int32_t* overflow,
+                         double* out_score, int64_t* out_idx, int32_t* out_valid,
+                         int32_t* cert, float* thr_next, void* stream);
+/* The j largest values of each row in descending order, -inf padded: out fp32 [rows, j] (j <= 4096).
+ * Row r holds min(counts[r], cols) valid values (counts == NULL: cols).  The j-th largest value of a corpus
+ * that is sharded over GPUs is the j-th largest of the union of the shards' top-j lists. */
+XMVE_API int xmve_row_topj(const float* vals, int64_t rows, int64_t cols, int64_t ld, const int32_t* counts,
+                  int32_t j, float* out, void* stream);
 
 /* ---- exact fp64 score matrix (small problems; the cal_error drop-in on float64 inputs) ----------
  * out[q, v] = alpha * <a_q, b_v>, a [nq, a_ld], b [nv, b_ld], out [nq, out_ld], all fp64, k columns.

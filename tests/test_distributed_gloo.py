@@ -37,6 +37,12 @@ def _worker(rank, world, port, out_dir):
     full = linas.cal_error(V, Q)
     ref = np.argsort(full, axis=1, kind="stable")[:, :k]
     ok = np.array_equal(mi.numpy(), ref) and np.allclose(ms.numpy(), -np.take_along_axis(full, ref, axis=1), atol=1e-15)
+    # the collectives of the shard-aware search pipeline (engine.search_shards), on gloo
+    comm = distributed.GroupComm()
+    g = comm.gather(torch.full((3, 2), float(rank)))
+    ok = ok and g.shape == (world, 3, 2) and all(bool((g[r] == r).all()) for r in range(world))
+    ok = ok and comm.max_(torch.tensor([rank, 5 - rank], dtype=torch.float64)).tolist() == [world - 1, 5.0]
+    ok = ok and comm.sum_int(hi - lo) == nv
     with open(os.path.join(out_dir, "rank%d" % rank), "w") as f:
         f.write("ok" if ok else "mismatch")
     dist.destroy_process_group()

@@ -28,9 +28,9 @@ def _operands(N, nq, nv, d, seed, layout_q=0, layout_v=0):
     a = torch.zeros((_rup(nq, 128), planes_q * dpad), dtype=torch.bfloat16, device="cuda")
     b = torch.zeros((_rup(nv, 256), planes_q * dpad), dtype=torch.bfloat16, device="cuda")
     st = N.stream_ptr()
-    N.call("xmve_prepare_rows", N.ptr(q), N.F32, nq, d, 1, d, None, 0, 0, None, N.ptr(a), a.stride(0), 0, layout_q, 1.0,
+    N.call("xmve_prepare_rows", N.ptr(q), N.F32, nq, d, 1, d, None, 0, 0, None, None, N.ptr(a), a.stride(0), 0, layout_q, 1.0,
            0, st)
-    N.call("xmve_prepare_rows", N.ptr(v), N.F32, nv, d, 1, d, None, 0, 0, None, N.ptr(b), b.stride(0), 0, layout_v, 1.0,
+    N.call("xmve_prepare_rows", N.ptr(v), N.F32, nv, d, 1, d, None, 0, 0, None, None, N.ptr(b), b.stride(0), 0, layout_v, 1.0,
            0, st)
     return q, v, a, b
 
@@ -46,8 +46,9 @@ def test_prepare_rows(N, n, d, frames, dtype):
     op = torch.full((n, 3 * dpad + 64), 7.0, dtype=torch.bfloat16, device="cuda")
     raw = torch.zeros((n, d + 4), dtype=torch.float32, device="cuda")
     nrm = torch.zeros(n, dtype=torch.float64, device="cuda")
+    res = torch.zeros(n, dtype=torch.float32, device="cuda")
     N.call("xmve_prepare_rows", N.ptr(x), N.F64 if dtype == torch.float64 else N.F32, n, d, frames, frames * d,
-           N.ptr(raw), raw.stride(0), 4, N.ptr(nrm), N.ptr(op), op.stride(0), 64, N.OP_X3_CORPUS, 0.5, 0,
+           N.ptr(raw), raw.stride(0), 4, N.ptr(nrm), N.ptr(res), N.ptr(op), op.stride(0), 64, N.OP_X3_CORPUS, 0.5, 0,
            N.stream_ptr())
     pooled = x.float() if frames == 1 else (x.float().sum(dim=1) / frames)
     ref_norm = torch.linalg.vector_norm(pooled.double(), dim=1)
@@ -63,6 +64,11 @@ def test_prepare_rows(N, n, d, frames, dtype):
     if dpad > d:
         assert torch.all(op[:, 64 + d:64 + dpad] == 0)        # zero-filled padding of each plane
     assert float((ref_norm - nrm).abs().max()) < 1e-4
+    # measured quantisation residual of the hi plane: || 0.5 * x_hat - bf16(0.5 * x_hat) ||^2, rounded up
+    exact = 0.5 * (raw[:, 4:4 + d].double() / nrm[:, None])
+    ref_res = ((exact - hi.double()) ** 2).sum(1)
+    assert torch.all(res.double() >= ref_res * (1 - 1e-6)) and torch.all(res.double() <= ref_res * (1 + 1e-5) + 1e-30)
+    assert torch.all(res.double().sqrt() <= 0.5 * 2.0 ** -8 * 1.0001)      # never above the worst-case rounding bound
 
 
 SHAPES = [(1000, 1000, 1536), (77, 333, 100), (128, 256, 64), (129, 257, 192), (60, 70000, 2048), (513, 5000, 640)]
@@ -170,6 +176,22 @@ def test_row_kth(N, rows, cols):
         a1 = srt[j1 - 1] - 0.5 if n >= j1 else torch.tensor(float("-inf"), device="cuda")
         a2 = srt[j2 - 1] if n >= j2 else torch.tensor(float("-inf"), device="cuda")
         assert out[r].item() == torch.maximum(a1, a2).item()
+
+
+@pytest.mark.parametrize("rows,cols,j", [(40, 5000, 64), (9, 50, 101), (3, 3000, 1000)])
+def test_row_topj(N, rows, cols, j):
+    g = torch.Generator(device="cuda").manual_seed(15)
+    x = torch.randn((rows, cols + 3), generator=g, device="cuda")
+    x[0, :10] = 0.75                                         # ties
+    counts = torch.randint(1, cols + 1, (rows,), generator=g, device="cuda", dtype=torch.int32)
+    counts[-1] = cols
+    out = torch.full((rows, j), 7.0, device="cuda")
+    N.call("xmve_row_topj", N.ptr(x), rows, cols, x.stride(0), N.ptr(counts), j, N.ptr(out), N.stream_ptr())
+    for r in range(rows):
+        n = int(counts[r])
+        ref = torch.sort(x[r, :n], descending=True).values[:j]
+        assert torch.equal(out[r, :len(ref)], ref)
+        assert torch.all(out[r, len(ref):] == float("-inf"))
 
 
 def test_select_topk_and_merge(N):

@@ -241,6 +241,41 @@ def test_sharded_search_equals_single_store(X):
     assert torch.equal(m_i, i_full) and torch.equal(m_s, s_full)
 
 
+def test_search_shards_one_global_threshold(X):
+    """The shard-aware pipeline (3 shards of one process; the multi-GPU path with the gathers done in place):
+    identical to one store, and every shard appends only about its share of the candidates."""
+    nv, nq, k = 300000, 96, 100
+    dims, w = (256, 64), (0.7, 0.3)
+    V, Q = X.synth.gaussian(31, nv, sum(dims)), X.synth.gaussian(32, nq, sum(dims))
+    full = X.engine.CorpusStore(nv, dims).add(torch.from_numpy(V))
+    st_full = {}
+    s_full, i_full = full.search(torch.from_numpy(Q), k, weights=w, stats=st_full)
+    shards = []
+    for r in range(3):
+        lo, hi = X.distributed.shard_range(nv, 3, r)
+        shards.append(X.engine.CorpusStore(hi - lo, dims, index_offset=lo).add(torch.from_numpy(V[lo:hi])))
+    excl = np.where(np.arange(nq) % 3 == 0, i_full[:, 0].cpu().numpy(), -1)
+    st_sh = {}
+    s_sh, i_sh = X.engine.search_shards(shards, torch.from_numpy(Q), k, weights=w, stats=st_sh)
+    assert torch.equal(i_sh, i_full) and torch.equal(s_sh, s_full)
+    total_full = float(st_full["cand_count"][0].float().mean())
+    total_sh = sum(float(c.float().mean()) for c in st_sh["cand_count"])
+    assert total_sh < 1.6 * total_full                     # not 3x: the threshold is global, not per shard
+    assert 5e-4 < st_sh["eps"] < 0.6 * X.engine.EPS_X1      # measured bound, well under the a-priori worst case
+    # exclusion + an empty shard in the list
+    shards.append(X.engine.CorpusStore(8, dims, index_offset=nv))
+    s_e, i_e = X.engine.search_shards(shards, torch.from_numpy(Q), k, weights=w, exclude=excl)
+    s_f, i_f = full.search(torch.from_numpy(Q), k, weights=w, exclude=excl)
+    assert torch.equal(i_e, i_f) and torch.equal(s_e, s_f)
+    # small-corpus branch (fp64 matrices per shard + merge): 3 shards of a 9 000-row corpus
+    small = [X.engine.CorpusStore(3000, dims, index_offset=3000 * r).add(torch.from_numpy(V[3000 * r:3000 * (r + 1)]))
+             for r in range(3)]
+    s_a, i_a = X.engine.search_shards(small, torch.from_numpy(Q), 7, weights=w)
+    one = X.engine.CorpusStore(9000, dims).add(torch.from_numpy(V[:9000]))
+    s_b, i_b = one.search(torch.from_numpy(Q), 7, weights=w)
+    assert torch.equal(i_a, i_b) and torch.allclose(s_a, s_b, rtol=0, atol=1e-14)
+
+
 def test_planted_neighbours_found_at_1m(X):
     """1M-row corpus generated on the device: every query's planted near-duplicate must be rank 1 and the
     returned scores must be sorted; the corpus permuted gives the same answer (order independence)."""

@@ -237,6 +237,17 @@ def peaks():
         return 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
 
 
+def ncu_traffic(nv_local):
+    """DRAM bytes per FILTER launch from the committed ncu --set full capture of this configuration (or None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)
+        rec = t.get(str(int(nv_local)))
+        return (rec["bytes"], rec["source"]) if rec else (None, None)
+    except Exception:
+        return None, None
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -319,6 +330,11 @@ def run_b200_arm(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     engine.N.call = orig_call
+    # one extra, untimed step with phase marks: where the step goes (reported, not part of any timing above)
+    st = {}
+    distributed.sharded_search(store, q_dev, k, weights=WEIGHTS, n_total=args.nv, stats=st)
+    phases = {kx: round(v, 3) for kx, v in st.get("phases_ms", {}).items()}
+    cand_mean = float(sum(c.float().mean() for c in st.get("cand_count", [])))
 
     if rank == 0:
         ms_step = ms_total / args.steps
@@ -327,6 +343,7 @@ def run_b200_arm(args):
         filt_avg = sum(filt_ms) / max(len(filt_ms), 1)
         flops = 2.0 * nq * (hi - lo) * sum(DIMS)
         achieved = flops / (filt_avg * 1e-3) / 1e12 if filt_avg > 0 else 0.0
+        traffic, traffic_src = ncu_traffic(hi - lo)
         line = {
             "metric": "text->video queries/sec at top-100", "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -340,9 +357,13 @@ def run_b200_arm(args):
             "gpu_launches": launches,
             "roofline": {"kernel": "score_kernel<FILTER> (tcgen05 score + threshold filter)", "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "launch_ms": filt_avg, "launches_timed": len(filt_ms),
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes": 2 * (hi - lo + nq) * sum(DIMS) + 8 * nq * k,
+                         "algorithmic_flops": flops, "peak_source": peak_src, "launch_ms": filt_avg, "launches_timed": len(filt_ms),
                          "share_of_step": filt_avg * len(filt_ms) / max(ms_total, 1e-9)},
             "clocks": clocks,
+            "stages": {"phases_ms": phases, "candidates_per_query_this_rank": cand_mean, "eps": st.get("eps"),
+                       "reruns": st.get("reruns", 0)},
         }
         if world == 1 and not args.skip_cpu_baseline:
             v, secs, sample = cpu_reference_sample(args.nv, nq)

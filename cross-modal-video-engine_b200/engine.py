@@ -282,6 +282,28 @@ def measured_eps(dq, dv, wts, n_space, k_len):
     return e
 
 
+class _Phases:
+    """CUDA-event marks at the phase boundaries of a search (only when the caller passes ``stats``)."""
+
+    def __init__(self, on):
+        self.on, self.marks = on, []
+
+    def mark(self, name):
+        if self.on:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((name, e))
+
+    def result(self):
+        if len(self.marks) < 2:
+            return {}
+        self.marks[-1][1].synchronize()
+        out = {}
+        for (_, a), (name, b) in zip(self.marks[:-1], self.marks[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
 class SoloComm:
     """The collective interface of :func:`search_shards` for a single process (world size 1)."""
     world = 1
@@ -352,7 +374,10 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
     if n_total == 0:
         raise ValueError("empty corpus")
     wts = _weights(weights, n_space)
+    ph = _Phases(stats is not None)
+    ph.mark("start")
     a_op, q_raw, q_norm, q_res, nq = ref.prepare_queries(queries, wts)
+    ph.mark("prepare_queries")
     if nq == 0:
         return (torch.empty((0, k), dtype=torch.float64, device=dev), torch.empty((0, k), dtype=torch.int64, device=dev))
     excl = None
@@ -382,6 +407,7 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
             else EPS_X1 * max(1.0, sum(abs(w) for w in wts))
     else:
         eps = float(eps) * max(1.0, sum(abs(w) for w in wts))
+    ph.mark("eps_sync")
     kk = k_eff + (1 if excl is not None else 0)               # one extra in case the excluded row is among them
     pl = plan(kk, n_total)
     live = [s for s in stores if s.n]
@@ -396,6 +422,7 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
             tops = [torch.full((nq, big_j), float("-inf"), dtype=torch.float32, device=dev)]
         thr = _row_kth(_union(tops, comm), None, pl["j"], 2.0 * eps, pl["j_cap"])
     del samples
+    ph.mark("sample_threshold")
     cap = pl["cap"] if solo else max(2048, min(pl["cap"], 1 << int(math.ceil(math.log2(4.0 * pl["cap"] / n_shards)))))
     rows = None                                               # None = all rows; else LongTensor of rows to re-run
     for attempt in range(12):
@@ -410,7 +437,9 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
             thr_sub = thr[rows].contiguous()
             ex_sub = excl[rows].contiguous() if excl is not None else None
         # 3: fused score + threshold filter on every local shard
+        ph.mark("alloc")
         cands = [s._filter(a_sub, n_sub, thr_sub, cap) for s in live]
+        ph.mark("filter")
         # 4: nothing below (kk-th largest approximate candidate score) - 2 eps can reach the top-k
         if solo:
             bound = _row_kth(cands[0][1], cands[0][0], kk, 2.0 * eps, 0)
@@ -419,6 +448,7 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
             if not tops:
                 tops = [torch.full((n_sub, kk), float("-inf"), dtype=torch.float32, device=dev)]
             bound = _row_kth(_union(tops, comm), None, kk, 2.0 * eps, 0)
+        ph.mark("bound")
         # 5: exact rescore + selection
         if solo:
             s_, i_, cert, thr_next = live[0]._rescore_select(q_sub, qn_sub, n_sub, k_eff, wts, ex_sub, cands[0], bound,
@@ -437,11 +467,13 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
             s_, i_, cert, thr_next = _merge(_union([p[0] for p in parts], comm), _union([p[1] for p in parts], comm),
                                             k_eff, thr=thr_sub, eps=eps, overflow=over)
             over = over != 0
+        ph.mark("rescore_select_merge")
         if stats is not None and rows is None:
             stats["eps"] = eps
             stats["cap"] = cap
             stats["cand_count"] = [c[0] for c in cands]
         bad = torch.nonzero(cert == 0).flatten()              # device -> host sync (identical on every rank)
+        ph.mark("certify_sync")
         if rows is None:
             out_s[:, :k_eff] = s_
             out_i[:, :k_eff] = i_
@@ -467,6 +499,8 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
     else:
         raise N.XmveError("search: %d row(s) could not be certified after 12 passes (increase eps headroom "
                           "or candidate capacity; heavy score ties?)" % int(rows.numel()))
+    if stats is not None:
+        stats["phases_ms"] = ph.result()
     return out_s, out_i
 
 

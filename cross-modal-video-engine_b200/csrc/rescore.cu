@@ -28,7 +28,7 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// One block per query row; its warps walk the row's candidate slots.
+// gridDim.y blocks per query row (more when there are few rows); their warps walk the row's candidate slots.
 __global__ void __launch_bounds__(RS_WARPS * 32)
 rescore_kernel(const float* __restrict__ q_raw, int64_t nq, int64_t q_ld, const double* __restrict__ q_norm,
                const float* __restrict__ v_raw, int64_t nv, int64_t v_ld, const double* __restrict__ v_norm,
@@ -44,7 +44,7 @@ rescore_kernel(const float* __restrict__ q_raw, int64_t nq, int64_t q_ld, const 
   const int n = min(cand_count[q], cap);
   const float bnd = bound ? bound[q] : -CUDART_INF_F;
   const bool vec = (v_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(v_raw) & 15u) == 0);
-  for (int c = warp; c < n; c += RS_WARPS) {                   // slots >= n are never read downstream
+  for (int c = blockIdx.y * RS_WARPS + warp; c < n; c += gridDim.y * RS_WARPS) {   // slots >= n are never read
     double res = -CUDART_INF;
     if (cand_score[q * cap + c] >= bnd) {
       const int64_t v = cand_idx[q * cap + c];
@@ -146,7 +146,14 @@ extern "C" int xmve_rescore(const float* q_raw, int64_t nq, int64_t q_ld, const 
   XMVE_REQUIRE(sp.off[0] == 0 && dtot <= q_ld && dtot <= v_ld, "rescore: offsets exceed the raw row length");
   if (dtot > 8192) return fail(XMVE_ERR_LIMIT, "rescore: total raw dim %d > 8192", dtot);
   if (nq == 0) return XMVE_OK;
-  rescore_kernel<<<static_cast<unsigned>(nq), RS_WARPS * 32, dtot * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  // few query rows (AVS: 60): split every row's candidates over several blocks so that all SMs gather
+  int64_t split = (4 * 148 + nq - 1) / nq;
+  if (split > 64) split = 64;
+  if (split > (cap + RS_WARPS - 1) / RS_WARPS) split = (cap + RS_WARPS - 1) / RS_WARPS;
+  if (split < 1) split = 1;
+  if (nq > 2147483647) return fail(XMVE_ERR_LIMIT, "rescore: too many query rows");
+  const dim3 grid(static_cast<unsigned>(nq), static_cast<unsigned>(split));
+  rescore_kernel<<<grid, RS_WARPS * 32, dtot * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       q_raw, nq, q_ld, q_norm, v_raw, nv, v_ld, v_norm, sp, norm_mode, cand_score, cand_idx, cand_count, cap, bound,
       exact);
   return launch_status("rescore_kernel");

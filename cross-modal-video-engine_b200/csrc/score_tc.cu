@@ -6,7 +6,7 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B swizzle, multi-stage smem ring)
 //   warp 1      MMA issuer     (tcgen05.mma, fp32 accumulators in TMEM; one elected thread)
 //   warp 2      TMEM allocator (512 columns = two 256-column accumulator slots)
-//   warps 4..   epilogue       (tcgen05.ld, one query row per thread)
+//   warps 4-11  epilogue       (tcgen05.ld, one query row per thread; two warps share each TMEM lane quarter)
 // Two epilogues share the main loop:
 //   STORE   out = alpha * S                                   (cal_error / sampling pass)
 //   FILTER  per-row window (lo, hi]: count scores above hi, append (score, index) of scores inside
@@ -61,7 +61,10 @@ struct Cfg {
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + NB * B_BYTES;   // 48 KB (wide) / 32 KB (pair) / 48 KB (single)
   static constexpr int STAGES = PAIR ? (NB == 2 ? 4 : 6) : 4;
-  static constexpr int THREADS = 128 + 128 * NB;               // 4 control warps + 4 epilogue warps per sub-tile
+  static constexpr int THREADS = 128 + 256;                    // 4 control warps + 8 epilogue warps
+  static constexpr int EPI_COLS = NB == 2 ? BN : BN / 2;       // columns of a slot drained by one epilogue warp:
+                                                               // wide: 4 warps per sub-tile; else two warps per
+                                                               // TMEM lane quarter split the slot's 256 columns
   static constexpr int PARK_BYTES = (THREADS - 128) * 8 * 8;   // STG (score, index) pairs per epilogue thread
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + PARK_BYTES;
   static constexpr int TILE_M = BM * CTAS;                     // query rows per tile
@@ -200,20 +203,20 @@ __device__ __forceinline__ void store_chunk(const Params& p, const uint32_t (&v)
   }
 }
 
-// One 128-row x 256-column accumulator slot -> STORE or FILTER (this thread owns query row st.row).  The TMEM
+// COLS columns of one 128-row accumulator slot -> STORE or FILTER (this thread owns query row st.row).  The TMEM
 // loads are software-pipelined: chunk c+1 is in flight while chunk c is examined.
-template <int MODE>
+template <int MODE, int COLS>
 __device__ __forceinline__ void epilogue_slot(const Params& p, uint32_t taddr, RowState& st, int64_t col0) {
   uint32_t v0[32], v1[32];
   ptx::tmem_ld_32x32(taddr, v0);
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; c += 2) {
+  for (int c = 0; c < COLS / 32; c += 2) {
     ptx::tmem_ld_wait();
     ptx::tmem_ld_32x32(taddr + (c + 1) * 32, v1);
     if (MODE == MODE_STORE) store_chunk(p, v0, st.row, col0 + c * 32);
     else filter_chunk(p, v0, st, col0 + c * 32);
     ptx::tmem_ld_wait();
-    if (c + 2 < BN / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, v0);
+    if (c + 2 < COLS / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, v0);
     if (MODE == MODE_STORE) store_chunk(p, v1, st.row, col0 + (c + 1) * 32);
     else filter_chunk(p, v1, st, col0 + (c + 1) * 32);
   }
@@ -248,7 +251,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
     }
     for (int a = 0; a < ACC_SLOTS; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);                        // one tcgen05.commit
-      ptx::mbar_init(&tempty_bar[a], 4 * C::CTAS);             // one arrival per epilogue warp (of both CTAs)
+      ptx::mbar_init(&tempty_bar[a], (BN / C::EPI_COLS) * 4 * C::CTAS);   // one arrival per warp draining the slot
     }
     ptx::fence_barrier_init();
   }
@@ -355,7 +358,9 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
   } else if (warp >= EPI_WARP0) {
     // ================================ epilogue ====================================
     const int quarter = warp & 3;                              // TMEM lane quarter this warp may read
-    const int sub = (warp - EPI_WARP0) >> 2;                   // sub-tile (accumulator slot) of the wide tile
+    const int grp = (warp - EPI_WARP0) >> 2;                   // wide: sub-tile (slot); else: half of the slot's columns
+    const int sub = NB == 2 ? grp : 0;
+    const int col_in_slot = NB == 2 ? 0 : grp * C::EPI_COLS;
     const int row_in_tile = static_cast<int>(rank) * BM + quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     RowState st;
@@ -365,7 +370,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
     uint32_t acc_phase = 0;
     for (int64_t u = worker; u < p.n_units; u += n_workers) {
       const Unit un = decode_unit(p, u, worker);
-      const int64_t col0 = static_cast<int64_t>(un.t) * C::TILE_N + sub * BN;
+      const int64_t col0 = static_cast<int64_t>(un.t) * C::TILE_N + sub * BN + col_in_slot;
       for (int i = 0; i < un.len; ++i) {
         const int slot = NB == 1 ? acc : sub;
         st.row = static_cast<int64_t>(un.mt(i)) * C::TILE_M + row_in_tile;
@@ -377,7 +382,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
         }
         ptx::mbar_wait(&tfull_bar[slot], acc_phase);
         ptx::tc_fence_after_sync();
-        epilogue_slot<MODE>(p, tmem_base + lane_addr + slot * BN, st, col0);
+        epilogue_slot<MODE, C::EPI_COLS>(p, tmem_base + lane_addr + slot * BN + col_in_slot, st, col0);
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) {                                       // one arrival per warp on the LEADER's barrier

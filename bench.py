@@ -290,10 +290,15 @@ def run_b200_arm(args):
     def step_device():
         return distributed.sharded_search(store, q_dev, k, weights=WEIGHTS, n_total=args.nv)
 
+    r_lo, r_hi = distributed.shard_range(nq, world, rank)   # result rows this rank hands back to the host
+
     def step_e2e():
-        s, i = distributed.sharded_search(store, q_host, k, weights=WEIGHTS, n_total=args.nv)
-        out_s_host.copy_(s, non_blocking=True)
-        out_i_host.copy_(i, non_blocking=True)
+        # host buffers in, host buffers out: the batch crosses PCIe once per node (each rank uploads its slice,
+        # NVLink all-gather), every rank returns its slice of the result rows
+        q = distributed.upload_rows(q_host, device=device)
+        s, i = distributed.sharded_search(store, q, k, weights=WEIGHTS, n_total=args.nv)
+        out_s_host[r_lo:r_hi].copy_(s[r_lo:r_hi], non_blocking=True)
+        out_i_host[r_lo:r_hi].copy_(i[r_lo:r_hi], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return s, i
 
@@ -353,7 +358,9 @@ def run_b200_arm(args):
                        "k": k, "parallelism": "corpus rows sharded over %d GPU(s), queries replicated" % world,
                        "l2": "inputs (>= 5 GB bf16 corpus operand per GPU) exceed the 126 MB L2; no flush needed"},
             "e2e": {"value": nq / (ms_e2e / args.steps * 1e-3), "unit": "queries/s",
-                    "h2d_bytes_per_step": q_host.numel() * 4, "d2h_bytes_per_step": nq * k * 16},
+                    "h2d_bytes_per_step": q_host.numel() * 4, "d2h_bytes_per_step": nq * k * 16,
+                    "note": "bytes are node totals: every rank uploads 1/N of the query batch (NVLink all-gather "
+                            "completes it) and returns 1/N of the result rows"},
             "gpu_launches": launches,
             "roofline": {"kernel": "score_kernel<FILTER> (tcgen05 score + threshold filter)", "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,

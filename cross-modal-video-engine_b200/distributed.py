@@ -45,6 +45,28 @@ class GroupComm:
         return int(t.item())
 
 
+def upload_rows(host_rows, group=None, device=None):
+    """Host -> device copy of a row batch that every rank holds on the host (the query batch of a serving step):
+    each rank copies only ITS slice over PCIe and the slices are all-gathered over NVLink, so the node moves the
+    batch across PCIe once instead of once per GPU (8 x 64 MB per step at 8192 x 2048 fp32 otherwise).
+    Returns the full ``[n, d]`` device tensor on every rank."""
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return host_rows.to(device, non_blocking=True)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = host_rows.shape[0]
+    per = (n + world - 1) // world
+    lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+    full = torch.empty((world * per,) + tuple(host_rows.shape[1:]), dtype=host_rows.dtype, device=device)
+    mine = torch.zeros((per,) + tuple(host_rows.shape[1:]), dtype=host_rows.dtype, device=device)
+    if hi > lo:
+        mine[: hi - lo].copy_(host_rows[lo:hi], non_blocking=True)
+    parts = list(full.view((world, per) + tuple(host_rows.shape[1:])).unbind(0))
+    dist.all_gather(parts, mine, group=group)
+    return full[:n]
+
+
 def gather_topk(scores, idx, group=None):
     """all_gather of local ``[nq, k]`` results -> ``[G, nq, k]`` on every rank (works on gloo and nccl)."""
     world = dist.get_world_size(group)

@@ -43,6 +43,8 @@ def _worker(rank, world, port, out_dir):
     ok = ok and g.shape == (world, 3, 2) and all(bool((g[r] == r).all()) for r in range(world))
     ok = ok and comm.max_(torch.tensor([rank, 5 - rank], dtype=torch.float64)).tolist() == [world - 1, 5.0]
     ok = ok and comm.sum_int(hi - lo) == nv
+    rows = torch.arange(37 * 3, dtype=torch.float32).reshape(37, 3)      # the same host batch on every rank
+    ok = ok and torch.equal(distributed.upload_rows(rows, device=torch.device("cpu")), rows)
     with open(os.path.join(out_dir, "rank%d" % rank), "w") as f:
         f.write("ok" if ok else "mismatch")
     dist.destroy_process_group()

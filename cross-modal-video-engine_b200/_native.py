@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libxmve.so")
 F32, F64 = 0, 1
 OP_X1, OP_X3_QUERY, OP_X3_CORPUS = 0, 1, 2
 NORM_PLAIN, NORM_EPS = 0, 1
+MEASURE_L1, MEASURE_L2, MEASURE_JACCARD = 0, 1, 2
 
 
 class XmveError(RuntimeError):
@@ -46,6 +47,7 @@ SIGNATURES = {
     "xmve_row_topj": [_p, _l, _l, _l, _p, _i32, _p, _p],
     "xmve_normalize_f64": [_p, _i, _l, _i, _l, _p, _l, _i, _p],
     "xmve_score_f64": [_p, _l, _l, _p, _l, _l, _i, _d, _p, _l, _p],
+    "xmve_pairwise_f64": [_p, _l, _l, _p, _l, _l, _i, _i, _d, _d, _p, _l, _p],
     "xmve_gt_ranks": [_p, _i, _l, _l, _l, _i, _p, _p, _l, _l, _i32, _p, _p],
     "xmve_rank_metrics": [_p, _p, _l, _l, _i, _i, _p, _p, _p, _p, _p, _p],
     "xmve_norm_score": [_p, _i, _l, _l, _l, _p, _l, _p, _p],
@@ -61,7 +63,7 @@ lib.xmve_last_error.restype = C.c_char_p
 launch_count = 0
 _LAUNCHES = {"xmve_prepare_rows": 1, "xmve_score_store": 1, "xmve_score_filter": 1, "xmve_row_kth": 1,
              "xmve_rescore": 1, "xmve_select_topk_i32": 1, "xmve_select_topk_i64": 1, "xmve_row_topj": 1, "xmve_normalize_f64": 1,
-             "xmve_score_f64": 1, "xmve_gt_ranks": 1, "xmve_rank_metrics": 1, "xmve_norm_score": 3}
+             "xmve_score_f64": 1, "xmve_pairwise_f64": 1, "xmve_gt_ranks": 1, "xmve_rank_metrics": 1, "xmve_norm_score": 3}
 
 
 def call(name, *args):

@@ -121,8 +121,87 @@ score_f64_kernel(const double* __restrict__ a, int64_t nq, int64_t a_ld, const d
     }
 }
 
+// ---- non-cosine measures of cal_error (evaluation.py:22-35): tiled pairwise distances on the CUDA cores --------
+// out[q, v] = alpha * f(a_q, b_v) + beta with f = sum|a-b| (L1), sqrt(sum (a-b)^2) (L2) or sum min / sum max (jaccard).
+template <int MEASURE>
+__global__ void __launch_bounds__(256)
+pairwise_kernel(const double* __restrict__ a, int64_t nq, int64_t a_ld, const double* __restrict__ b, int64_t nv,
+                int64_t b_ld, int k, double alpha, double beta, double* __restrict__ out, int64_t out_ld) {
+  __shared__ double as[TK][TM + 1];
+  __shared__ double bs[TK][TN + 1];
+  const int64_t q0 = static_cast<int64_t>(blockIdx.y) * TM, v0 = static_cast<int64_t>(blockIdx.x) * TN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4] = {};
+  double acc2[MEASURE == XMVE_MEASURE_JACCARD ? 4 : 1][4] = {};
+  for (int k0 = 0; k0 < k; k0 += TK) {
+    for (int e = threadIdx.x; e < TM * TK; e += 256) {
+      const int r = e / TK, c = e % TK;
+      as[c][r] = (q0 + r < nq && k0 + c < k) ? a[(q0 + r) * a_ld + k0 + c] : 0.0;
+      bs[c][r] = (v0 + r < nv && k0 + c < k) ? b[(v0 + r) * b_ld + k0 + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < TK; ++c) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        av[i] = as[c][ty * 4 + i];
+        bv[i] = bs[c][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (MEASURE == XMVE_MEASURE_L1) {
+            acc[i][j] += fabs(av[i] - bv[j]);
+          } else if (MEASURE == XMVE_MEASURE_L2) {
+            const double t = av[i] - bv[j];
+            acc[i][j] = fma(t, t, acc[i][j]);
+          } else {
+            acc[i][j] += fmin(av[i], bv[j]);
+            acc2[MEASURE == XMVE_MEASURE_JACCARD ? i : 0][j] += fmax(av[i], bv[j]);
+          }
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t q = q0 + ty * 4 + i, v = v0 + tx * 4 + j;
+      if (q < nq && v < nv) {
+        double f = acc[i][j];
+        if (MEASURE == XMVE_MEASURE_L2) f = sqrt(f);
+        if (MEASURE == XMVE_MEASURE_JACCARD) f = f / acc2[MEASURE == XMVE_MEASURE_JACCARD ? i : 0][j];
+        out[q * out_ld + v] = alpha * f + beta;
+      }
+    }
+}
+
 }  // namespace
 }  // namespace xmve
+
+extern "C" int xmve_pairwise_f64(const double* a, int64_t nq, int64_t a_ld, const double* b, int64_t nv, int64_t b_ld,
+                                 int k, int measure, double alpha, double beta, double* out, int64_t out_ld,
+                                 void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  XMVE_REQUIRE(a && b && out && nq >= 0 && nv >= 0 && k > 0 && a_ld >= k && b_ld >= k && out_ld >= nv,
+               "pairwise_f64: bad arguments");
+  XMVE_REQUIRE(measure >= XMVE_MEASURE_L1 && measure <= XMVE_MEASURE_JACCARD, "pairwise_f64: unknown measure %d", measure);
+  if (nq == 0 || nv == 0) return XMVE_OK;
+  dim3 grid(static_cast<unsigned>((nv + TN - 1) / TN), static_cast<unsigned>((nq + TM - 1) / TM));
+  if (grid.y > 65535) return fail(XMVE_ERR_LIMIT, "pairwise_f64: more than %d query rows; chunk the call", 65535 * TM);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (measure == XMVE_MEASURE_L1)
+    pairwise_kernel<XMVE_MEASURE_L1><<<grid, 256, 0, st>>>(a, nq, a_ld, b, nv, b_ld, k, alpha, beta, out, out_ld);
+  else if (measure == XMVE_MEASURE_L2)
+    pairwise_kernel<XMVE_MEASURE_L2><<<grid, 256, 0, st>>>(a, nq, a_ld, b, nv, b_ld, k, alpha, beta, out, out_ld);
+  else
+    pairwise_kernel<XMVE_MEASURE_JACCARD><<<grid, 256, 0, st>>>(a, nq, a_ld, b, nv, b_ld, k, alpha, beta, out, out_ld);
+  return launch_status("pairwise_kernel");
+}
 
 extern "C" int xmve_rescore(const float* q_raw, int64_t nq, int64_t q_ld, const double* q_norm, const float* v_raw,
                             int64_t nv, int64_t v_ld, const double* v_norm, int n_space, const int32_t* space_off,

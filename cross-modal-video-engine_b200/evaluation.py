@@ -5,11 +5,14 @@ return conventions), running on hand-written sm_100a kernels through libxmve.
 * ``cal_error(videos, captions)``     evaluation.py:17-36 (cosine branch) -> errors = -cosine, [Nq, Nv]
 * ``cal_error_batch(...)``            evaluation.py:41-72 (cosine branch is identical)
 * ``cal_simi(captions, videos)``      evaluation.py:75-84 (+cosine; NOTE the swapped argument order)
+* ``encode_vid`` / ``encode_text``    evaluation.py:87-171, without the per-batch ``.cpu().numpy()`` round trip: the
+  embeddings stay on the encoder's device as one float64 tensor (the reference keeps float64 arrays too), ready for
+  ``cal_error`` / ``CorpusStore.add``
 
 dtype follows the input, like the reference: float64 arrays (what ``encode_vid`` / ``encode_text``
 produce, evaluation.py:102,134) are scored by the exact fp64 kernel; float32 arrays by the tcgen05
-kernel with split-bf16 (x3) operands, |error| ~ 1e-6.  Only ``measure='cosine'`` is on the hot path
-(SURVEY.md section 8a A2); the cdist / jaccard measures are out of scope and raise.
+kernel with split-bf16 (x3) operands, |error| ~ 1e-6.  ``measure='cosine'`` is the hot path (SURVEY.md section 8a
+A2); the cdist / jaccard measures (section 8f row 4) run on a tiled CUDA-core kernel in fp64.
 """
 from __future__ import annotations
 
@@ -94,22 +97,91 @@ def score_matrix(queries, corpus, alpha, norm_mode=N.NORM_PLAIN):
     return out
 
 
+#: measure -> (kernel measure, alpha as a function of the dim, beta); evaluation.py:22-35
+_PAIRWISE = {
+    'euclidean': (N.MEASURE_L2, lambda d: 1.0, 0.0), 'l2': (N.MEASURE_L2, lambda d: 1.0, 0.0),
+    'l1': (N.MEASURE_L1, lambda d: 1.0, 0.0),
+    'l1_norm': (N.MEASURE_L1, lambda d: -1.0 / d, -1.0), 'l2_norm': (N.MEASURE_L2, lambda d: -1.0 / d, -1.0),
+    'jaccard': (N.MEASURE_JACCARD, lambda d: -1.0, 0.0),
+}
+
+
+def pairwise_matrix(queries, corpus, measure):
+    """The scipy ``cdist`` / ``jaccard_sim`` branches of ``cal_error`` on the CUDA cores, in fp64.  ``cdist`` always
+    returns float64; ``jaccard_sim`` runs on ``torch.Tensor(...)`` = float32 in the reference (returned as float32)."""
+    q, _ = _host_in(queries)
+    v, _ = _host_in(corpus)
+    nq, d = q.shape
+    nv = v.shape[0]
+    assert v.shape[1] == d, "embedding dims differ"
+    if measure == 'jaccard':                                     # torch.Tensor(x): values rounded to float32 first
+        q, v = q.float(), v.float()
+    q, v = q.double().contiguous(), v.double().contiguous()
+    code, alpha, beta = _PAIRWISE[measure]
+    out = torch.empty((nq, nv), dtype=torch.float64, device=q.device)
+    step = 1 << 21
+    for q0 in range(0, nq, step):
+        q1 = min(nq, q0 + step)
+        N.call("xmve_pairwise_f64", N.ptr(q[q0:]), q1 - q0, d, N.ptr(v), nv, d, d, code, float(alpha(d)), float(beta),
+               N.ptr(out[q0:]), nv, N.stream_ptr())
+    return out.float() if measure == 'jaccard' else out
+
+
 def cal_error(videos, captions, measure='cosine'):
-    """errors[q, v] = -cos(caption q, video v); evaluation.py:17-21."""
-    if measure != 'cosine':
-        raise NotImplementedError("measure=%r is outside the B200 hot path (cosine only)" % (measure,))
+    """errors[q, v] = -cos(caption q, video v) (evaluation.py:17-21) or one of the distance measures (:22-35)."""
     was_numpy = not torch.is_tensor(captions)
-    return _out(score_matrix(captions, videos, -1.0), was_numpy)
+    if measure == 'cosine':
+        return _out(score_matrix(captions, videos, -1.0), was_numpy)
+    if measure not in _PAIRWISE:
+        raise ValueError("unknown measure %r" % (measure,))
+    return _out(pairwise_matrix(captions, videos, measure), was_numpy)
 
 
 def cal_error_batch(videos, captions, measure='cosine', batch_size=2000):
-    """evaluation.py:41-45: the cosine branch does not batch, so this is ``cal_error``."""
+    """evaluation.py:41-72: same results as ``cal_error`` (the reference batches only to bound the memory of its
+    broadcasted jaccard; the kernel here never materialises the [Nq, Nv, D] tensor)."""
     return cal_error(videos, captions, measure)
 
 
 def cal_simi(captions, videos, measure='cosine'):
     """+cos(caption, video); evaluation.py:75-79 (captions FIRST here, unlike ``cal_error``)."""
-    if measure != 'cosine':
-        raise NotImplementedError("measure=%r is outside the B200 hot path (cosine only)" % (measure,))
     was_numpy = not torch.is_tensor(captions)
+    if measure == 'jaccard':                                     # evaluation.py:80-83: +jaccard_sim
+        return _out(-pairwise_matrix(captions, videos, 'jaccard'), was_numpy)
+    if measure != 'cosine':
+        raise ValueError("cal_simi knows 'cosine' and 'jaccard' (evaluation.py:75-84), got %r" % (measure,))
     return _out(score_matrix(captions, videos, 1.0), was_numpy)
+
+
+def _encode(encoder, data_loader, n_inputs, return_ids):
+    embeddings = None
+    n = len(data_loader.dataset)
+    ids = [''] * n
+    for batch in data_loader:
+        datas, (idxs, data_ids) = batch[:n_inputs], batch[n_inputs:]
+        emb = encoder(*datas)
+        if embeddings is None:                                   # np.zeros((N, D)) in the reference: float64
+            embeddings = torch.zeros((n, emb.size(1)), dtype=torch.float64, device=emb.device)
+        rows = torch.as_tensor(list(idxs), dtype=torch.int64, device=emb.device)
+        embeddings[rows] = emb.detach().to(torch.float64)        # stays on the device: no PCIe round trip
+        for j, idx in enumerate(idxs):
+            ids[idx] = data_ids[j]
+        del datas
+    if return_ids:
+        return embeddings, ids
+    return embeddings
+
+
+def encode_vid(encoder, data_loader, return_ids=True):
+    """evaluation.py:87-115: embeddings ``[len(dataset), D]`` scattered by dataset index, as ONE device tensor."""
+    return _encode(encoder, data_loader, 1, return_ids)
+
+
+def encode_text(encoder, data_loader, style, return_ids=True):
+    """evaluation.py:118-171: ``style='distill_from_best_model'`` batches are ``(datas, idxs, ids)``, ``style='GT'``
+    batches carry ``support_datas`` as a second encoder input."""
+    if style == 'distill_from_best_model':
+        return _encode(encoder, data_loader, 1, return_ids)
+    if style == 'GT':
+        return _encode(encoder, data_loader, 2, return_ids)
+    return None                                                  # the reference falls through for other styles

@@ -170,6 +170,16 @@ XMVE_API int xmve_normalize_f64(const void* src, int src_dtype, int64_t n, int d
 XMVE_API int xmve_score_f64(const double* a, int64_t nq, int64_t a_ld, const double* b, int64_t nv, int64_t b_ld,
                    int k, double alpha, double* out, int64_t out_ld, void* stream);
 
+/* ---- non-cosine measures of cal_error (LINAS-engine/evaluation.py:22-35; scipy cdist / loss.jaccard_sim) -------
+ * out[q, v] = alpha * f(a_q, b_v) + beta,  f = sum_i |a_i - b_i| (L1), sqrt(sum_i (a_i - b_i)^2) (L2) or
+ * sum_i min(a_i, b_i) / sum_i max(a_i, b_i) (JACCARD); a [nq, a_ld], b [nv, b_ld], out [nq, out_ld] fp64, k columns.
+ * 'l1' / 'l2' / 'euclidean': alpha = 1, beta = 0; 'l1_norm' / 'l2_norm': alpha = -1/k, beta = -1; 'jaccard': alpha = -1.
+ * CUDA-core kernel (ALU-bound); at most 65535 * 64 query rows per call.
+ */
+enum { XMVE_MEASURE_L1 = 0, XMVE_MEASURE_L2 = 1, XMVE_MEASURE_JACCARD = 2 };
+XMVE_API int xmve_pairwise_f64(const double* a, int64_t nq, int64_t a_ld, const double* b, int64_t nv, int64_t b_ld,
+                      int k, int measure, double alpha, double beta, double* out, int64_t out_ld, void* stream);
+
 /* ---- K4: bit-exact rank / metric kernels --------------------------------------------------------
  * errors is the caller's [n_row, n_col] matrix (fp32/fp64, smaller = better, as cal_error returns).
  * gt_off[n_query+1], gt_ids[] is a CSR of ground-truth positions per query.

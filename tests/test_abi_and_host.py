@@ -110,3 +110,34 @@ def test_search_plan_is_sane():
         assert 1 <= p["j"] <= p["j_cap"] <= p["n_sample"]
         assert 2048 <= p["cap"] <= 32768 and p["j_cap"] * p["step"] <= p["cap"]
         assert p["n_sample"] <= 0.02 * n or n < 1_000_000     # the sampling pass stays a small fraction
+
+
+def test_encode_vid_and_text_keep_the_reference_layout():
+    """encode_vid / encode_text (evaluation.py:87-171) with a toy encoder and loader: rows scattered by dataset index,
+    float64, ids in dataset order -- as one tensor on the encoder's device instead of a host array."""
+    from cross_modal_video_engine_b200 import evaluation
+
+    class DS:
+        def __len__(self):
+            return 7
+
+    class Loader:
+        dataset = DS()
+
+        def __init__(self, with_support):
+            self.with_support = with_support
+
+        def __iter__(self):
+            for idxs in ([4, 0, 6], [2, 5], [1, 3]):
+                datas = torch.tensor([[float(i), 1.0] for i in idxs])
+                ids = ["id%d" % i for i in idxs]
+                yield (datas, datas * 2, idxs, ids) if self.with_support else (datas, idxs, ids)
+
+    emb, ids = evaluation.encode_vid(lambda x: (x * 3).float(), Loader(False))
+    assert emb.dtype == torch.float64 and ids == ["id%d" % i for i in range(7)]
+    assert emb.tolist() == [[3.0 * i, 3.0] for i in range(7)]
+    emb2 = evaluation.encode_text(lambda x, s: (x + s).float(), Loader(True), "GT", return_ids=False)
+    assert emb2.tolist() == [[3.0 * i, 3.0] for i in range(7)]
+    emb3, _ = evaluation.encode_text(lambda x: x.float(), Loader(False), "distill_from_best_model")
+    assert emb3[:, 0].tolist() == [float(i) for i in range(7)]
+    assert evaluation.encode_text(lambda x: x, Loader(False), "other") is None

@@ -1,0 +1,93 @@
+"""Ingest formats against goldens minted by the reference's own ``util/txt2bin.py``
+and ``basic/bigfile.py`` (oracle/make_golden_io.py).  Host logic: CPU only, except the two ``gpu`` tests."""
+import filecmp
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from cross_modal_video_engine_b200 import corpus_io
+
+TOY = os.path.join(GOLDEN, "bigfile_toy")
+
+
+@pytest.fixture(scope="module")
+def rec():
+    with open(os.path.join(GOLDEN, "bigfile_toy.json")) as f:
+        return json.load(f)
+
+
+def _parse_txt():
+    names, rows = [], []
+    for line in open(os.path.join(GOLDEN, "bigfile_toy.txt")):
+        e = line.split()
+        names.append(e[0])
+        rows.append([float(x) for x in e[1:]])
+    return names, np.array(rows, dtype=np.float32)
+
+
+def test_bigfile_reader_matches_reference(rec):
+    bf = corpus_io.BigFile(TOY)
+    assert bf.shape() == rec["shape"] and len(bf.names) == rec["shape"][0]
+    names, vecs = bf.read(rec["requests"]["by_name"])
+    assert [names, vecs] == rec["by_name"]                     # sorted by row, unknown + duplicate names dropped
+    names, vecs = bf.read(rec["requests"]["by_index"], isname=False)
+    assert [names, vecs] == rec["by_index"]
+    assert bf.read_one("video1_1") == rec["read_one"]
+    assert list(bf.read(["nope"])) == rec["empty"]
+    assert bf.rows().shape == tuple(rec["shape"]) and bf.rows().dtype == np.float32
+
+
+def test_bigfile_writer_matches_txt2bin(tmp_path, rec):
+    names, feats = _parse_txt()
+    assert names == rec["names"]
+    n = corpus_io.write_bigfile(str(tmp_path / "bf"), names, feats)
+    assert n == rec["shape"][0]                                 # the duplicated name and the NaN row are dropped
+    for fn in ("shape.txt", "id.txt", "feature.bin"):
+        assert filecmp.cmp(os.path.join(TOY, fn), str(tmp_path / "bf" / fn), shallow=False), fn
+
+
+def test_video_data_round_trip_on_host(tmp_path):
+    embs = np.random.default_rng(3).standard_normal((17, 9))
+    ids = ["video%d" % i for i in range(17)]
+    p = str(tmp_path / "video_data.pt")
+    corpus_io.save_video_data(p, embs, ids)
+    d = torch.load(p, weights_only=False)                       # what inference.py:58-60 reads back
+    assert np.array_equal(d["video_embs"], embs) and d["video_ids"] == ids
+
+
+@pytest.mark.gpu
+def test_bigfile_to_store_and_search(tmp_path):
+    from cross_modal_video_engine_b200 import synth
+    from oracle import linas
+    nv, d = 30000, 96
+    V, Q = synth.clustered(61, nv, d), synth.clustered(62, 40, d)
+    names = ["shot%07d" % i for i in range(nv)]
+    corpus_io.write_bigfile(str(tmp_path / "bf"), names, V)
+    store, ids = corpus_io.BigFile(str(tmp_path / "bf")).to_store(chunk_rows=7001)   # ragged chunks, staging reuse
+    assert ids == names and store.n == nv
+    assert torch.equal(store.raw[:nv, :d].cpu(), torch.from_numpy(V))
+    s, i = store.search(torch.from_numpy(Q), 10)
+    err = linas.cal_error(V.astype(np.float64), Q.astype(np.float64))
+    ref = np.argsort(err, axis=1, kind="stable")[:, :10]
+    np.testing.assert_array_equal(i.cpu().numpy(), ref)
+
+
+@pytest.mark.gpu
+def test_video_data_pt_to_store(tmp_path):
+    from cross_modal_video_engine_b200 import synth
+    from oracle import linas
+    V = synth.gaussian(71, 5000, 64).astype(np.float64)         # encode_vid keeps float64 arrays (evaluation.py:102)
+    ids = ["video%d" % i for i in range(len(V))]
+    p = str(tmp_path / "video_data.pt")
+    corpus_io.save_video_data(p, V, ids)
+    store, got = corpus_io.load_video_data(p)
+    assert got == ids and store.n == len(V)
+    q = synth.gaussian(72, 3, 64).astype(np.float64)
+    s, i = store.search(q, 5)
+    err = linas.cal_error(V, q)
+    np.testing.assert_array_equal(i.cpu().numpy(), np.argsort(err, axis=1, kind="stable")[:, :5])
+    np.testing.assert_allclose(s.cpu().numpy(), -np.sort(err, axis=1)[:, :5], rtol=0, atol=1e-12)

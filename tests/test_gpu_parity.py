@@ -72,8 +72,28 @@ def test_l2norm_and_norm_score(X, manifest):
         out = X.validate.norm_score(g["errors_" + tag])
         assert out.dtype == g["norm_score_" + tag].dtype
         np.testing.assert_array_equal(out, g["norm_score_" + tag])          # same IEEE operations, same order
-    with pytest.raises(NotImplementedError):
-        X.evaluation.cal_error(V, Q, "jaccard")
+    with pytest.raises(ValueError):
+        X.evaluation.cal_error(V, Q, "chebyshev")
+
+
+def test_non_cosine_measures_match_reference_golden(X):
+    """evaluation.py:22-35 (scipy cdist: float64 out) and loss.jaccard_sim (torch float32) on the reference's outputs."""
+    g = load_golden("measures")
+    V, Q = g["V"], g["Q"]
+    for m in ("euclidean", "l1", "l2", "l1_norm", "l2_norm"):
+        e = X.evaluation.cal_error(V, Q, m)
+        assert e.dtype == np.float64 and e.shape == g["err_" + m].shape
+        np.testing.assert_allclose(e, g["err_" + m], rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(X.evaluation.cal_error(V.astype(np.float32), Q.astype(np.float32), m), g["err_" + m],
+                                   rtol=1e-13, atol=1e-13)              # cdist widens float32 inputs to double
+    e = X.evaluation.cal_error(V, Q, "jaccard")
+    assert e.dtype == np.float32
+    np.testing.assert_allclose(e, g["err_jaccard"], rtol=2e-6, atol=0)  # the reference sums in float32
+    np.testing.assert_allclose(X.evaluation.cal_error_batch(V, Q, "jaccard", batch_size=20), g["batch_jaccard"],
+                               rtol=2e-6, atol=0)
+    np.testing.assert_allclose(X.evaluation.cal_simi(Q, V, "jaccard"), g["simi_jaccard"], rtol=2e-6, atol=0)
+    t = X.evaluation.cal_error(torch.from_numpy(V), torch.from_numpy(Q), "l1")
+    assert t.is_cuda and t.dtype == torch.float64                       # tensors in, device tensor out
 
 
 # ---- metrics.py / validate.py: bit-exact given the same matrix ---------------------------------------

@@ -472,6 +472,9 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
             stats["eps"] = eps
             stats["cap"] = cap
             stats["cand_count"] = [c[0] for c in cands]
+            ar = torch.arange(cap, device=dev)
+            stats["rescored_per_query"] = sum(
+                float(((ar[None, :] < c[0][:, None]) & (c[1] >= bound[:, None])).sum()) for c in cands) / n_sub
         bad = torch.nonzero(cert == 0).flatten()              # device -> host sync (identical on every rank)
         ph.mark("certify_sync")
         if rows is None:

@@ -123,7 +123,7 @@ XMVE_API int xmve_row_kth(const float* vals, int64_t rows, int64_t cols, int64_t
  * the arithmetic of cal_error on float64 inputs (evaluation.py:19-21) up to rounding order.
  * space_off[n_space+1] (HOST array) are column offsets into the raw rows, weights[n_space] is a HOST
  * array, q_norm/v_norm are DEVICE [n_space, n] fp64.  exact[q, c] is written for c < cand_count[q] only.
- * norm_mode as in xmve_prepare_rows.  Limit: total raw dim <= 8192.
+ * norm_mode as in xmve_prepare_rows.  Limit: total raw dim <= 6000.
  */
 XMVE_API int xmve_rescore(const float* q_raw, int64_t nq, int64_t q_ld, const double* q_norm,
                  const float* v_raw, int64_t nv, int64_t v_ld, const double* v_norm,

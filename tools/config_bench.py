@@ -35,7 +35,7 @@ def run(tag, nv, nq, d, k, reps=10):
     byts = 2.0 * (nv + nq) * d + 8.0 * nq * k
     print("%s: %.3f ms/search  %.0f queries/s  %.1f TFLOP/s  %.0f GB/s(alg)  phases %s  cand/row %.0f eps %.2e" % (
         tag, ms, nq / ms * 1e3, flops / ms / 1e9, byts / ms / 1e6,
-        {k_: round(v, 3) for k_, v in st["phases_ms"].items()}, float(st["cand_count"][0].float().mean()), st["eps"]),
+        {k_: round(v, 3) for k_, v in st["phases_ms"].items()}, float(st["cand_count"][0].float().mean()), st["eps"]), "rescored/row %.0f" % st["rescored_per_query"],
         flush=True)
     del store
     torch.cuda.empty_cache()
@@ -47,5 +47,7 @@ if __name__ == "__main__":
         run("C3 60x1.08Mx2048 k=1000", 1_080_000, 60, 2048, 1000)
     if "c4" in which:
         run("C4 4096x1Mx640 k=100", 1_000_000, 4096, 640, 100)
+    if "c5s" in which:
+        run("8192x2Mx2048 k=100", 2_000_000, 8192, 2048, 100, reps=3)
     if "c1" in which:
         run("1x1Mx2048 k=10 (online query)", 1_000_000, 1, 2048, 10)

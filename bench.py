@@ -61,7 +61,7 @@ def parse():
 _SAMPLE_CACHE = {}
 
 
-def cpu_reference_sample(nv_total, nq_total, nq_s=32, nv_s=400_000):
+def cpu_reference_sample(nv_total, nq_total, nq_s=128, nv_s=500_000):
     """Time the reference's path on a bounded sample and extrapolate each stage to the full workload.
 
     Stages, as ``inference.py:78-80`` runs them per call: l2norm of BOTH sides (evaluation.py:19-20; the corpus

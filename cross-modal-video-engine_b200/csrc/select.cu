@@ -20,8 +20,9 @@ __device__ __forceinline__ float key_float(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// j-th largest (1-based) of vals[0..n); -inf if n < j.  All threads of the block must call it.
-__device__ float block_kth_largest(const float* __restrict__ vals, int64_t n, int j, uint32_t* hist, uint32_t* bcast) {
+// j-th largest (1-based) of get(0..n); -inf if n < j.  All threads of the block must call it.
+template <typename Get>
+__device__ float block_kth_largest_of(Get get, int64_t n, int j, uint32_t* hist, uint32_t* bcast) {
   if (j <= 0 || n < j) return -CUDART_INF_F;
   uint32_t prefix = 0, mask = 0;
   uint32_t remaining = static_cast<uint32_t>(j);
@@ -29,7 +30,7 @@ __device__ float block_kth_largest(const float* __restrict__ vals, int64_t n, in
     for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
     __syncthreads();
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint32_t k = float_key(vals[i]);
+      const uint32_t k = float_key(get(i));
       if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 0xffu], 1u);
     }
     __syncthreads();
@@ -50,6 +51,10 @@ __device__ float block_kth_largest(const float* __restrict__ vals, int64_t n, in
     __syncthreads();
   }
   return key_float(prefix);
+}
+
+__device__ float block_kth_largest(const float* __restrict__ vals, int64_t n, int j, uint32_t* hist, uint32_t* bcast) {
+  return block_kth_largest_of([vals](int64_t i) { return vals[i]; }, n, j, hist, bcast);
 }
 
 __global__ void __launch_bounds__(256)
@@ -146,22 +151,45 @@ select_topk_kernel(const double* __restrict__ score, const IdxT* __restrict__ id
     n_in = min(static_cast<int64_t>(counts[r]), cols);
   }
   if (overflow != nullptr && overflow[r] != 0) cand_overflow = true;   // a shard's candidate list overflowed
+  __shared__ uint32_t sel_hist[256];
+  __shared__ uint32_t sel_bcast[2];
   if (threadIdx.x == 0) n_valid_s = 0;
   __syncthreads();
   const int64_t excl = exclude ? exclude[r] : -1;
+  const double* srow = score + r * cols;
+  const IdxT* irow = idx ? idx + r * cols : nullptr;
+  // valid entry i -> its score, anything else -> -inf
+  auto value = [&](int64_t i) -> double {
+    const double s = srow[i];
+    const IdxT id = irow ? irow[i] : static_cast<IdxT>(i);            // idx == NULL: column number
+    return (s > -CUDART_INF && !(exclude && static_cast<int64_t>(id) + idx_offset == excl)) ? s : -CUDART_INF;
+  };
+  for (int64_t i = threadIdx.x; i < n_in; i += blockDim.x)
+    if (value(i) > -CUDART_INF) atomicAdd(&n_valid_s, 1);
+  __syncthreads();
+  const int n_all = n_valid_s;                                         // every valid entry of the row
+  // More valid entries than the sort holds (dense neighbourhoods: thousands of items within eps of the k-th
+  // best): keep only those whose score, rounded to float, reaches the k-th largest rounded score.  Rounding is
+  // monotone, so the kept set contains the exact top-k; it can exceed the capacity only through > pmax scores
+  // that agree to float precision with the k-th.
+  float floor_f = -CUDART_INF_F;
+  if (n_all > pmax)
+    floor_f = block_kth_largest_of([&](int64_t i) { return __double2float_rn(value(i)); }, n_in, k, sel_hist, sel_bcast);
+  __syncthreads();
+  if (threadIdx.x == 0) n_valid_s = 0;
+  __syncthreads();
   for (int64_t i = threadIdx.x; i < n_in; i += blockDim.x) {
-    const double s = score[r * cols + i];
-    const IdxT id = idx ? idx[r * cols + i] : static_cast<IdxT>(i);   // idx == NULL: column number
-    if (s > -CUDART_INF && !(exclude && static_cast<int64_t>(id) + idx_offset == excl)) {
+    const double s = value(i);
+    if (s > -CUDART_INF && __double2float_rn(s) >= floor_f) {
       const int pos = atomicAdd(&n_valid_s, 1);
       if (pos < pmax) {
         keys[pos] = s;
-        ids[pos] = id;
+        ids[pos] = irow ? irow[i] : static_cast<IdxT>(i);
       }
     }
   }
   __syncthreads();
-  const int n_valid = n_valid_s;
+  const int n_valid = n_valid_s;                                       // entries kept for the sort
   const int n = min(n_valid, pmax);
   int P = 1;
   while (P < n) P <<= 1;
@@ -194,7 +222,7 @@ select_topk_kernel(const double* __restrict__ score, const IdxT* __restrict__ id
     out_idx[r * k + i] = ok ? static_cast<int64_t>(ids[i]) + idx_offset : -1;
   }
   if (threadIdx.x == 0) {
-    if (out_valid) out_valid[r] = n_valid;
+    if (out_valid) out_valid[r] = n_all;
     if (cert != nullptr) {
       const float t = thr[r];
       const bool enough = n >= k && n_valid <= pmax;

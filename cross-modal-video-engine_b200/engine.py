@@ -424,6 +424,7 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
     del samples
     ph.mark("sample_threshold")
     cap = pl["cap"] if solo else max(2048, min(pl["cap"], 1 << int(math.ceil(math.log2(4.0 * pl["cap"] / n_shards)))))
+    n_shard_max = max(s.n for s in live) if live else 1
     rows = None                                               # None = all rows; else LongTensor of rows to re-run
     for attempt in range(12):
         if rows is None:
@@ -475,6 +476,7 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
             ar = torch.arange(cap, device=dev)
             stats["rescored_per_query"] = sum(
                 float(((ar[None, :] < c[0][:, None]) & (c[1] >= bound[:, None])).sum()) for c in cands) / n_sub
+            ph.mark("stats_bookkeeping")
         bad = torch.nonzero(cert == 0).flatten()              # device -> host sync (identical on every rank)
         ph.mark("certify_sync")
         if rows is None:
@@ -497,8 +499,11 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
         if stats is not None:
             stats["reruns"] = stats.get("reruns", 0) + 1
             stats["rerun_rows"] = stats.get("rerun_rows", 0) + int(rows.numel())
-        if bool(stuck.any()) and cap < 32768:
-            cap = min(32768, cap * 4)                         # overflow that a tighter threshold cannot fix
+        if bool(stuck.any()):
+            # overflow that a tighter threshold cannot fix (dense neighbourhoods within eps of the k-th best): grow
+            # the lists -- for the few rows left they may grow until they hold a whole shard (cannot overflow then)
+            room = max(32768, min(1 << int(math.ceil(math.log2(n_shard_max))), (1 << 27) // max(int(rows.numel()), 1)))
+            cap = min(room, cap * 4)
     else:
         raise N.XmveError("search: %d row(s) could not be certified after 12 passes (increase eps headroom "
                           "or candidate capacity; heavy score ties?)" % int(rows.numel()))

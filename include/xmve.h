@@ -140,7 +140,9 @@ XMVE_API int xmve_rescore(const float* q_raw, int64_t nq, int64_t q_ld, const do
  * kth_score - eps >= thr[r] -- then no corpus item outside the candidate set can belong to the
  * top-k given |approx - exact| <= eps.  thr_next[r] is the threshold to re-run an uncertified row
  * with (kth - eps when k entries were found; bound[r] = approximate kth of the retained candidates
- * - 2 eps after a candidate-list overflow).  Limit: at most 16384 valid entries per row.
+ * - 2 eps after a candidate-list overflow).  The sort holds 16384 entries per row; rows with more valid entries
+ * are first cut at the k-th largest score rounded to float (a superset of the exact top-k), so only > 16384
+ * scores that agree with the k-th to float precision defeat it (reported as not certified).
  */
 XMVE_API int xmve_select_topk_i32(const double* score, const int32_t* idx, int64_t rows, int64_t cols,
                          const int32_t* counts, int64_t idx_offset, const int64_t* exclude, int32_t k,

@@ -235,6 +235,36 @@ def test_select_topk_and_merge(N):
     assert torch.equal(r_s, out_s) and torch.equal(r_i, out_i)
 
 
+def test_select_topk_more_valid_entries_than_the_sort_holds(N):
+    """40 000 valid scores per row (the sort holds 16 384): the kernel first cuts at the k-th largest float-rounded
+    score, which keeps a superset of the exact top-k -- including a block of exact ties across the k boundary."""
+    rows, cols, k = 6, 40000, 100
+    g = torch.Generator(device="cuda").manual_seed(18)
+    score = torch.randn((rows, cols), generator=g, device="cuda", dtype=torch.float64)
+    score[1] = 0.9 + 1e-9 * torch.randn(cols, generator=g, device="cuda", dtype=torch.float64)   # one float value
+    score[2, 500:700] = 5.0                                                                     # 200 exact ties on top
+    idx = torch.stack([torch.randperm(cols, generator=g, device="cuda") for _ in range(rows)]).int()
+    counts = torch.full((rows,), cols, dtype=torch.int32, device="cuda")
+    out_s = torch.empty((rows, k), dtype=torch.float64, device="cuda")
+    out_i = torch.empty((rows, k), dtype=torch.int64, device="cuda")
+    valid = torch.empty(rows, dtype=torch.int32, device="cuda")
+    thr = torch.full((rows,), -10.0, device="cuda")
+    cert = torch.empty(rows, dtype=torch.int32, device="cuda")
+    nxt = torch.empty(rows, device="cuda")
+    N.call("xmve_select_topk_i32", N.ptr(score), N.ptr(idx), rows, cols, N.ptr(counts), 0, None, k, N.ptr(thr), 1e-3,
+           None, N.ptr(out_s), N.ptr(out_i), N.ptr(valid), N.ptr(cert), N.ptr(nxt), N.stream_ptr())
+    assert (valid == cols).all()
+    for r in range(rows):
+        if r == 1:                       # 40 000 scores that agree to float precision: reported as not certified
+            assert int(cert[r]) == 0
+            continue
+        order = torch.argsort(idx[r].long(), stable=True)                  # index ascending ...
+        s_sorted = score[r][order]
+        top = torch.argsort(s_sorted, descending=True, stable=True)[:k]    # ... then score descending, stable
+        assert torch.equal(out_s[r], s_sorted[top]) and torch.equal(out_i[r], idx[r].long()[order][top])
+        assert int(cert[r]) == 1
+
+
 def test_rescore_is_fp64_exact(N):
     import ctypes as C
     nq, nv, cap = 33, 5000, 64

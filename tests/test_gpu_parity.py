@@ -204,6 +204,40 @@ def test_search_recovers_when_threshold_is_wrong(X):
     assert stats.get("reruns", 0) >= 1
 
 
+def test_search_exact_ties_are_ordered_by_index(X):
+    """Every corpus vector appears three times: the top-k is full of exact score ties, also across the k boundary.
+    Engine order = (score desc, index asc) = what a stable argsort of the reference's error row gives."""
+    nu, d, nq, k = 40000, 192, 80, 50
+    U, Q = X.synth.gaussian(41, nu, d), X.synth.gaussian(42, nq, d)
+    perm = np.random.default_rng(43).permutation(3 * nu)
+    V = np.concatenate([U, U, U])[perm]
+    store = X.engine.CorpusStore(len(V), (d,)).add(torch.from_numpy(V))
+    s, i = store.search(torch.from_numpy(Q), k)
+    ref_idx, ref_s = _oracle_topk(V, Q, k)
+    np.testing.assert_array_equal(i.cpu().numpy(), ref_idx)
+    np.testing.assert_allclose(s.cpu().numpy(), ref_s, rtol=0, atol=1e-13)
+    assert (ref_s[:, 0] == ref_s[:, 2]).all()                   # the ties are really there
+
+
+def test_search_survives_candidate_overflow(X):
+    """Dense neighbourhoods: 30 000 rows sit within a few degrees of each of four query directions, far more than
+    the candidate lists hold and invisible to the strided sample's order statistic for the other queries.  The
+    overflowed rows must be re-run with a higher threshold (or longer lists) and still come back exact."""
+    nv, nq, d, k = 200000, 64, 128, 100
+    rng = np.random.default_rng(9)
+    V = rng.standard_normal((nv, d)).astype(np.float32)
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    for qi in range(4):
+        rows = rng.choice(nv, size=30000, replace=False)
+        V[rows] = Q[qi] * 2.0 + 0.4 * rng.standard_normal((30000, d)).astype(np.float32)
+    store = X.engine.CorpusStore(nv, (d,)).add(torch.from_numpy(V))
+    stats = {}
+    s, i = store.search(torch.from_numpy(Q), k, stats=stats)
+    ref_idx, ref_s = _oracle_topk(V, Q, k)
+    np.testing.assert_array_equal(i.cpu().numpy(), ref_idx)
+    np.testing.assert_allclose(s.cpu().numpy(), ref_s, rtol=0, atol=1e-13)
+
+
 def test_search_edge_cases(X):
     V, Q = X.synth.gaussian(1, 37, 70), X.synth.gaussian(2, 5, 70)
     store = X.engine.CorpusStore(64, (70,)).add(V[:20]).add(V[20:])

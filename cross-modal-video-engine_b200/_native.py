@@ -51,6 +51,7 @@ SIGNATURES = {
     "xmve_gt_ranks": [_p, _i, _l, _l, _l, _i, _p, _p, _l, _l, _i32, _p, _p],
     "xmve_rank_metrics": [_p, _p, _l, _l, _i, _i, _p, _p, _p, _p, _p, _p],
     "xmve_norm_score": [_p, _i, _l, _l, _l, _p, _l, _p, _p],
+    "xmve_fuse_accumulate": [_p, _l, _p, _l, _i, _l, _l, _d, _i, _p],
 }
 for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name)
@@ -63,7 +64,7 @@ lib.xmve_last_error.restype = C.c_char_p
 launch_count = 0
 _LAUNCHES = {"xmve_prepare_rows": 1, "xmve_score_store": 1, "xmve_score_filter": 1, "xmve_row_kth": 1,
              "xmve_rescore": 1, "xmve_select_topk_i32": 1, "xmve_select_topk_i64": 1, "xmve_row_topj": 1, "xmve_normalize_f64": 1,
-             "xmve_score_f64": 1, "xmve_pairwise_f64": 1, "xmve_gt_ranks": 1, "xmve_rank_metrics": 1, "xmve_norm_score": 3}
+             "xmve_score_f64": 1, "xmve_pairwise_f64": 1, "xmve_gt_ranks": 1, "xmve_rank_metrics": 1, "xmve_norm_score": 3, "xmve_fuse_accumulate": 1}
 
 
 def call(name, *args):

@@ -260,6 +260,50 @@ extern "C" int xmve_rank_metrics(const int32_t* ranks, const int64_t* gt_off, in
   return launch_status("rank_metrics_kernel");
 }
 
+namespace xmve {
+namespace {
+// acc = w * e (first) or acc + w * e, each operation rounded separately like NumPy's (no fused multiply-add)
+template <typename T>
+__global__ void __launch_bounds__(256)
+fuse_kernel(T* __restrict__ acc, int64_t acc_ld, const T* __restrict__ e, int64_t e_ld, int64_t n_row, int64_t n_col,
+            T w, int first) {
+  const int64_t total = n_row * n_col;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / n_col, c = i % n_col;
+    const T x = e[r * e_ld + c];
+    T y;
+    if (sizeof(T) == 8) {
+      const double t = __dmul_rn(static_cast<double>(w), static_cast<double>(x));
+      y = static_cast<T>(first ? t : __dadd_rn(static_cast<double>(acc[r * acc_ld + c]), t));
+    } else {
+      const float t = __fmul_rn(static_cast<float>(w), static_cast<float>(x));
+      y = static_cast<T>(first ? t : __fadd_rn(static_cast<float>(acc[r * acc_ld + c]), t));
+    }
+    acc[r * acc_ld + c] = y;
+  }
+}
+}  // namespace
+}  // namespace xmve
+
+extern "C" int xmve_fuse_accumulate(void* acc, int64_t acc_ld, const void* e, int64_t e_ld, int dtype, int64_t n_row,
+                                    int64_t n_col, double w, int first, void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  XMVE_REQUIRE(acc && e && n_row >= 0 && n_col >= 0 && acc_ld >= n_col && e_ld >= n_col, "fuse_accumulate: bad arguments");
+  XMVE_REQUIRE(dtype == XMVE_F32 || dtype == XMVE_F64, "fuse_accumulate: dtype must be f32 or f64");
+  if (n_row == 0 || n_col == 0) return XMVE_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = 8 * sm_count();
+  if (dtype == XMVE_F32)
+    fuse_kernel<float><<<grid, 256, 0, st>>>(static_cast<float*>(acc), acc_ld, static_cast<const float*>(e), e_ld, n_row,
+                                             n_col, static_cast<float>(w), first);
+  else
+    fuse_kernel<double><<<grid, 256, 0, st>>>(static_cast<double*>(acc), acc_ld, static_cast<const double*>(e), e_ld,
+                                              n_row, n_col, w, first);
+  return launch_status("fuse_kernel");
+}
+
 extern "C" int xmve_norm_score(const void* errors, int dtype, int64_t n_row, int64_t n_col, int64_t ld, void* out,
                                int64_t out_ld, double* minmax_scratch, void* stream) {
   using namespace xmve;

@@ -153,6 +153,35 @@ def cal_simi(captions, videos, measure='cosine'):
     return _out(score_matrix(captions, videos, 1.0), was_numpy)
 
 
+def fused_errors(video_spaces, caption_spaces, weights, mode='weighted-cosine'):
+    """Multi-space fusion of error matrices (the reference keeps only vestiges: the
+    ``--space`` / ``--measure_2`` flags, ``norm_score``, teacher + student embedding pairs):
+
+    * ``'weighted-cosine'``: ``errors = sum_s w_s * cal_error(V_s, Q_s)``
+    * ``'norm_score'``     : ``errors = sum_s w_s * norm_score(cal_error(V_s, Q_s))`` (validate.py:7-11 per space)
+
+    One array per embedding space on each side; dtype and container follow the inputs like ``cal_error``.  For
+    corpora whose matrix cannot exist use ``CorpusStore(dims=(D_1, D_2, ...)).search(q, k, weights=...)``, which
+    folds the weights into ONE tensor-core contraction."""
+    from .validate import norm_score
+    if mode not in ('weighted-cosine', 'norm_score'):
+        raise ValueError(mode)
+    assert len(video_spaces) == len(caption_spaces) == len(weights) and len(weights) >= 1
+    was_numpy = not torch.is_tensor(caption_spaces[0])
+    acc = None
+    for s_i, (V, Q, w) in enumerate(zip(video_spaces, caption_spaces, weights)):
+        e = score_matrix(Q, V, -1.0)
+        if mode == 'norm_score':
+            e = norm_score(e)
+        if acc is None:
+            acc = torch.empty_like(e)
+        assert e.dtype == acc.dtype and e.shape == acc.shape, "spaces must agree in dtype and row counts"
+        if e.numel():
+            N.call("xmve_fuse_accumulate", N.ptr(acc), acc.stride(0), N.ptr(e), e.stride(0), _dt(e), e.shape[0], e.shape[1],
+                   float(w), 1 if s_i == 0 else 0, N.stream_ptr())
+    return _out(acc, was_numpy)
+
+
 def _encode(encoder, data_loader, n_inputs, return_ids):
     embeddings = None
     n = len(data_loader.dataset)

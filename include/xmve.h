@@ -213,6 +213,14 @@ XMVE_API int xmve_rank_metrics(const int32_t* ranks, const int64_t* gt_off, int6
 XMVE_API int xmve_norm_score(const void* errors, int dtype, int64_t n_row, int64_t n_col, int64_t ld,
                     void* out, int64_t out_ld, double* minmax_scratch, void* stream);
 
+/* ---- multi-space fusion of score matrices ---------------------------------
+ * acc = w * e (first != 0) or acc = acc + w * e, element-wise on [n_row, n_col] matrices of `dtype`, every
+ * multiplication and addition rounded on its own (what NumPy's `acc + w * e` does; no fused multiply-add), w
+ * rounded to `dtype` first.  Composes `errors = sum_s w_s * cal_error_s` and `sum_s w_s * norm_score(cal_error_s)`.
+ */
+XMVE_API int xmve_fuse_accumulate(void* acc, int64_t acc_ld, const void* e, int64_t e_ld, int dtype,
+                         int64_t n_row, int64_t n_col, double w, int first, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,33 @@ def test_l2norm_and_norm_score(X, manifest):
         X.evaluation.cal_error(V, Q, "chebyshev")
 
 
+@pytest.mark.parametrize("mode", ["weighted-cosine", "norm_score"])
+def test_fused_errors_matrix(X, mode):
+    """sum_s w_s * cal_error_s and sum_s w_s * norm_score(cal_error_s) against the oracle's
+    composition of the reference functions; the weighted sum itself is bit-exact given the same per-space matrices."""
+    dims, w = (96, 40), (0.6, 0.4)
+    V, Q = X.synth.clustered(81, 300, sum(dims)), X.synth.clustered(82, 170, sum(dims))
+    for cast, tol in ((np.float64, 2e-13), (np.float32, 3e-6)):
+        Vs = [V[:, :96].astype(cast), V[:, 96:].astype(cast)]
+        Qs = [Q[:, :96].astype(cast), Q[:, 96:].astype(cast)]
+        got = X.evaluation.fused_errors(Vs, Qs, w, mode)
+        ref = linas.fused_errors([v.astype(np.float64) for v in Vs], [q.astype(np.float64) for q in Qs], w, mode)
+        assert got.dtype == cast and got.shape == ref.shape
+        np.testing.assert_allclose(got, ref, rtol=0, atol=tol)
+    # bit-exactness of the fusion arithmetic: feed the oracle's per-space matrices through the kernel
+    import ctypes  # noqa: F401
+    e = [linas.cal_error(V[:, :96].astype(np.float64), Q[:, :96].astype(np.float64)),
+         linas.cal_error(V[:, 96:].astype(np.float64), Q[:, 96:].astype(np.float64))]
+    acc = torch.empty(e[0].shape, dtype=torch.float64, device="cuda")
+    for s_i, (m, ws) in enumerate(zip(e, w)):
+        t = torch.from_numpy(m).cuda()
+        X.native.call("xmve_fuse_accumulate", X.native.ptr(acc), acc.stride(0), X.native.ptr(t), t.stride(0), X.native.F64,
+                      t.shape[0], t.shape[1], float(ws), 1 if s_i == 0 else 0, X.native.stream_ptr())
+    np.testing.assert_array_equal(acc.cpu().numpy(), w[0] * e[0] + w[1] * e[1])
+    with pytest.raises(ValueError):
+        X.evaluation.fused_errors([V], [Q], [1.0], "max")
+
+
 def test_non_cosine_measures_match_reference_golden(X):
     """evaluation.py:22-35 (scipy cdist: float64 out) and loss.jaccard_sim (torch float32) on the reference's outputs."""
     g = load_golden("measures")

@@ -22,6 +22,33 @@ def search_avs(stores, queries, k=1000, weights=None, comm=None, n_total=None):
     return search_shards(stores, queries, k, weights=weights, comm=comm, n_total=n_total)
 
 
+def _list_ranks(idx, relevant, n_mem):
+    """1-based position of every relevant row in its query's ranked list (``n_mem + 1`` if absent) as a CSR:
+    returns ``(off int64 [nq+1], rank int32 [n_entries], device)``."""
+    idx = idx if torch.is_tensor(idx) else torch.as_tensor(np.asarray(idx))
+    dev = idx.device if idx.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    idx = idx.to(dev)
+    nq, kk = idx.shape
+    assert len(relevant) == nq, "one relevant set per query"
+    sizes = np.fromiter((len(r) for r in relevant), dtype=np.int64, count=nq)
+    off = np.zeros(nq + 1, dtype=np.int64)
+    np.cumsum(sizes, out=off[1:])
+    off_d = torch.from_numpy(off).to(dev)
+    if int(off[-1]) == 0:
+        return off_d, torch.zeros(1, dtype=torch.int32, device=dev), dev
+    rel = torch.from_numpy(np.concatenate([np.asarray(r, dtype=np.int64).reshape(-1) for r in relevant])).to(dev)
+    owner = torch.repeat_interleave(torch.arange(nq, device=dev), torch.from_numpy(sizes).to(dev))
+    # sort the (query, row) keys of the lists once, look every relevant row up
+    big = int(n_mem) + 1
+    keys = (torch.arange(nq, device=dev).unsqueeze(1) * big + idx.clamp(min=-1) + 1).reshape(-1)   # -1 pad -> slot 0
+    skeys, order = torch.sort(keys)
+    want = owner * big + rel + 1
+    pos = torch.searchsorted(skeys, want).clamp(max=skeys.numel() - 1)
+    found = skeys[pos] == want
+    rank = torch.where(found, order[pos] % kk + 1, torch.full_like(pos, big)).to(torch.int32)
+    return off_d, rank, dev
+
+
 def ap_at_k(idx, relevant, n_shots, k=None):
     """``APScorer(k).score`` of every query's ranked list against its relevant set, on the device.
 
@@ -32,31 +59,13 @@ def ap_at_k(idx, relevant, n_shots, k=None):
     with ``mAP = np.mean(ap)`` (``util/metrics.py:75-79`` style).
     """
     N.require_device()
-    idx = idx if torch.is_tensor(idx) else torch.as_tensor(np.asarray(idx))
-    dev = idx.device if idx.is_cuda else torch.device("cuda", torch.cuda.current_device())
-    idx = idx.to(dev)
     nq, kk = idx.shape
     k = kk if k is None else min(int(k), kk)
-    assert len(relevant) == nq, "one relevant set per query"
-    sizes = np.fromiter((len(r) for r in relevant), dtype=np.int64, count=nq)
-    off = np.zeros(nq + 1, dtype=np.int64)
-    np.cumsum(sizes, out=off[1:])
-    n_ent = int(off[-1])
+    off_d, rank, dev = _list_ranks(idx, relevant, n_shots)
     ap = torch.zeros(nq, dtype=torch.float64, device=dev)
-    if n_ent == 0 or nq == 0:
+    if nq == 0 or int(off_d[-1]) == 0:
         out = ap.cpu().numpy()
         return out, (np.mean(out) if nq else np.float64("nan"))
-    rel = torch.from_numpy(np.concatenate([np.asarray(r, dtype=np.int64).reshape(-1) for r in relevant])).to(dev)
-    owner = torch.repeat_interleave(torch.arange(nq, device=dev), torch.from_numpy(sizes).to(dev))
-    # position of every relevant shot in its query's list: sort (query, shot) keys of the lists once, look up
-    big = int(n_shots) + 1
-    keys = (torch.arange(nq, device=dev).unsqueeze(1) * big + idx.clamp(min=-1) + 1).reshape(-1)   # -1 pad -> slot 0
-    skeys, order = torch.sort(keys)
-    want = owner * big + rel + 1
-    pos = torch.searchsorted(skeys, want).clamp(max=skeys.numel() - 1)
-    found = skeys[pos] == want
-    rank = torch.where(found, order[pos] % kk + 1, torch.full_like(pos, big)).to(torch.int32)      # 1-based position
-    off_d = torch.from_numpy(off).to(dev)
     N.call("xmve_rank_metrics", N.ptr(rank), N.ptr(off_d), nq, int(n_shots), 0, int(k), None, N.ptr(ap), None, None,
            None, N.stream_ptr())
     out = ap.cpu().numpy()

@@ -140,6 +140,34 @@ def v2t_map(c2i, v2t_gts):
     return RankResult(c2i_t, v2t_gts).mean_ap()
 
 
+# ---- the same metrics from top-k lists (corpora whose score matrix cannot exist) -------------------------
+def eval_q2m_topk(idx, q2m_gts, n_m):
+    """``eval_q2m`` (util/metrics.py:124-157) from ranked top-k lists instead of the score matrix: ``idx`` int64
+    ``[n_q, k]`` from ``CorpusStore.search`` / ``sharded_search``, ``q2m_gts[i]`` the ground-truth rows of query i,
+    ``n_m`` the corpus size.  A query's rank is the best position of its ground truth in the list; beyond the list it
+    is only known to be ``> k``.  Returns ``(r1, r5, r10, medr, meanr, n_found)``: the recalls are exact whenever
+    ``k >= 10``; ``medr`` is exact when it falls inside the lists and ``inf`` otherwise; ``meanr`` is exact only if
+    every ground truth was found (``nan`` otherwise)."""
+    from . import _native as N_
+    from .avs import _list_ranks
+    N_.require_device()
+    n_q, k = idx.shape
+    off, rank, dev = _list_ranks(idx, [q2m_gts[i] for i in range(n_q)], n_m)
+    best = torch.empty(n_q, dtype=torch.int32, device=dev)
+    tallies = torch.zeros(4, dtype=torch.int64, device=dev)
+    hist = torch.zeros(n_m + 2, dtype=torch.int32, device=dev)
+    N_.call("xmve_rank_metrics", N_.ptr(rank), N_.ptr(off), n_q, int(n_m), 0, 0, N_.ptr(best), None, N_.ptr(tallies),
+            N_.ptr(tallies[3:]), N_.ptr(hist), N_.stream_ptr())
+    c1, c5, c10, rsum = (int(v) for v in tallies.cpu().tolist())
+    n_found = int((best <= k).sum())
+    r1, r5, r10 = 100.0 * c1 / n_q, 100.0 * c5 / n_q, 100.0 * c10 / n_q
+    medr = _median_from_hist(hist.cpu().numpy(), n_q)
+    if medr > k:
+        medr = np.float64("inf")
+    meanr = np.float64(rsum) / n_q if n_found == n_q else np.float64("nan")
+    return (r1, r5, r10, medr, meanr, n_found)
+
+
 # ---- legacy fixed-n_caption forms (never reached from cal_perf; SURVEY.md section 8a A13) ------------
 def _ranks0(c2i, gts, axis_cols):
     m = (c2i.T if not torch.is_tensor(c2i) else c2i.t()) if axis_cols else c2i

@@ -231,6 +231,24 @@ def test_search_recovers_when_threshold_is_wrong(X):
     assert stats.get("reruns", 0) >= 1
 
 
+def test_eval_q2m_from_topk_lists(X):
+    """R@1/5/10 and MedR from top-k lists == the reference's eval_q2m on the full matrix (planted captions)."""
+    V, Q, vid, cap, _ = X.synth.msrvtt_like(5, 30000, 1, 128, 4.5)
+    Q, cap = Q[:700], cap[:700]
+    store = X.engine.CorpusStore(len(V), (128,)).add(torch.from_numpy(V))
+    _, idx = store.search(torch.from_numpy(Q), 50)
+    _, t2v_gt = linas.get_gt(vid, cap)
+    gts = [t2v_gt[i] for i in range(len(Q))]
+    r1, r5, r10, medr, meanr, n_found = X.metrics.eval_q2m_topk(idx, gts, len(V))
+    ref = linas.eval_q2m(linas.cal_error(V.astype(np.float64), Q.astype(np.float64)), t2v_gt)
+    assert (r1, r5, r10) == tuple(ref[:3]) and 5.0 < r1 < 95.0
+    if ref[3] <= 50:
+        assert medr == ref[3]
+    else:
+        assert medr == np.inf
+    assert n_found < len(Q) and np.isnan(meanr)                 # some captions rank beyond the lists
+
+
 def test_search_exact_ties_are_ordered_by_index(X):
     """Every corpus vector appears three times: the top-k is full of exact score ties, also across the k boundary.
     Engine order = (score desc, index asc) = what a stable argsort of the reference's error row gives."""

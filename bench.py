@@ -276,7 +276,7 @@ def run_b200_arm(args):
     orig_call = _native.call
 
     def timed_call(name, *a):
-        if name == "xmve_score_filter":
+        if name == "xmve_score_filter" and a[6] == 1:      # the pass over the whole shard (not the sampled one)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             r = orig_call(name, *a)

@@ -39,7 +39,7 @@ SIGNATURES = {
     "xmve_sm_count": [],
     "xmve_prepare_rows": [_p, _i, _l, _i, _i, _l, _p, _l, _l, _p, _p, _p, _l, _l, _i, _f, _i, _p],
     "xmve_score_store": [_p, _l, _l, _p, _l, _l, _l, _i, _f, _p, _l, _p],
-    "xmve_score_filter": [_p, _l, _l, _p, _l, _l, _i, _p, _p, _p, _p, _p, _p, _i32, _p],
+    "xmve_score_filter": [_p, _l, _l, _p, _l, _l, _l, _i, _p, _p, _p, _p, _p, _p, _i32, _p],
     "xmve_row_kth": [_p, _l, _l, _l, _p, _i32, _f, _i32, _p, _p],
     "xmve_rescore": [_p, _l, _l, _p, _p, _l, _l, _p, _i, _p, _p, _i, _p, _p, _p, _i32, _p, _p, _p],
     "xmve_select_topk_i32": [_p, _p, _l, _l, _p, _l, _p, _i32, _p, _f, _p, _p, _p, _p, _p, _p, _p],

@@ -583,12 +583,12 @@ extern "C" int xmve_score_store(const void* a_op, int64_t nq, int64_t a_ld, cons
 }
 
 extern "C" int xmve_score_filter(const void* a_op, int64_t nq, int64_t a_ld, const void* b_op, int64_t nv,
-                                 int64_t b_ld, int k, const float* lo, const float* hi, int32_t* count_above,
-                                 int32_t* cand_count, float* cand_score, int32_t* cand_idx, int32_t cap,
-                                 void* stream) {
+                                 int64_t b_ld, int64_t b_row_step, int k, const float* lo, const float* hi,
+                                 int32_t* count_above, int32_t* cand_count, float* cand_score, int32_t* cand_idx,
+                                 int32_t cap, void* stream) {
   using namespace xmve;
   XMVE_DEVICE_OR_RETURN();
-  int s = check_operands(a_op, nq, a_ld, b_op, nv, b_ld, 1, k);
+  int s = check_operands(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k);
   if (s != XMVE_OK) return s;
   XMVE_REQUIRE(lo != nullptr && cand_count != nullptr && cand_score != nullptr && cand_idx != nullptr && cap > 0,
                "score_filter: lo / candidate buffers are required and cap must be > 0");
@@ -601,5 +601,5 @@ extern "C" int xmve_score_filter(const void* a_op, int64_t nq, int64_t a_ld, con
   p.cand_score = cand_score;
   p.cand_idx = cand_idx;
   p.cap = cap;
-  return launch<MODE_FILTER>(a_op, nq, a_ld, b_op, nv, b_ld, 1, k, p, static_cast<cudaStream_t>(stream));
+  return launch<MODE_FILTER>(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k, p, static_cast<cudaStream_t>(stream));
 }

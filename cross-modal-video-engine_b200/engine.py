@@ -6,20 +6,11 @@ Replaces, for a corpus that is encoded once and queried many times, the per-call
 ``evaluation.py:19-20``) and the 32-query ``1 - P @ index.T`` / ``torch.argsort`` blocks of
 ``MultiFusion/src/validate.py:65-113``.
 
-Pipeline of :meth:`CorpusStore.search` (all on the caller's CUDA stream, no host sync until the
-certification flags are read):
-
-1. K1  queries -> bf16 operand (per-space weight / norm folded in), fp32 raw copy, fp64 norms
-2. K2  STORE pass over every ``step``-th corpus row (strided TMA view)      -> score sample
-3.     radix select of the sample                                              -> per-row threshold
-4. K2  FILTER pass over the whole shard; the epilogue appends (score, index) above the threshold
-5.     radix select of the candidates' approximate scores                     -> rescore bound
-6.     exact fp64 rescore of the survivors from the raw fp32 rows
-7.     bitonic top-k of the exact scores + certification that nothing outside the candidate set
-       can belong to the top-k (given |bf16 score - exact| <= eps)
-8.     rows that are not certified are re-run with the threshold the kernel proposes.
-
-Corpora of at most ``small_nv`` rows skip 2-5: the fp64 score matrix is formed directly.
+The pipeline is :func:`search_shards` (its docstring lists the steps): K1 on the queries, a sampled per-query
+threshold, the fused tcgen05 score + threshold filter over the resident operand (the score matrix never reaches
+HBM), an exact fp64 rescore of the survivors, a bitonic top-k with a certificate that nothing outside the
+candidate set can belong to the top-k, and a re-run of the rare rows that miss the certificate.
+:meth:`CorpusStore.search` is the one-shard case; ``distributed.sharded_search`` joins the shards of several GPUs.
 """
 from __future__ import annotations
 
@@ -217,16 +208,33 @@ class CorpusStore:
                self.k, 1.0, N.ptr(sample), sample.stride(0), N.stream_ptr())
         return sample
 
-    def _filter(self, a_op, nq, thr, cap):
-        """K2 FILTER over the shard: candidates (approximate score, local row) above ``thr`` per query."""
+    def _filter(self, a_op, nq, thr, cap, step=1):
+        """K2 FILTER over the shard (or over every ``step``-th row): candidates (approximate score, local row --
+        sampled-row number when ``step > 1``) above ``thr`` per query."""
         dev = self.device
+        rows = (self.n + step - 1) // step
         cand_count = torch.zeros((nq,), dtype=torch.int32, device=dev)
         cand_score = torch.empty((nq, cap), dtype=torch.float32, device=dev)
         cand_idx = torch.empty((nq, cap), dtype=torch.int32, device=dev)
-        N.call("xmve_score_filter", N.ptr(a_op), nq, a_op.stride(0), N.ptr(self.op), self.n, self.op.stride(0),
+        N.call("xmve_score_filter", N.ptr(a_op), nq, a_op.stride(0), N.ptr(self.op), rows, self.op.stride(0), step,
                self.k, N.ptr(thr), None, None, N.ptr(cand_count), N.ptr(cand_score), N.ptr(cand_idx), cap,
                N.stream_ptr())
         return cand_count, cand_score, cand_idx
+
+    def _sample_top(self, a_op, nq, step, big_j):
+        """The largest scores of the ``step``-strided sample of this shard WITHOUT writing the sample matrix:
+        a coarse STORE pass (every ``r * step``-th row, a few thousand columns) gives a per-query floor ``thr0``
+        that about ``4 * big_j`` of the fine sample's scores exceed; a FILTER pass over the fine sample keeps those.
+        Returns ``(scores fp32 [nq, cap_s], counts int32 [nq], thr0 fp32 [nq])``; rows whose count is below
+        ``big_j`` (the floor came out too high -- vanishingly rare) are handled by the caller through ``thr0``."""
+        n_s = (self.n + step - 1) // step
+        r = max(2, min(16, n_s // 2048))
+        coarse = self._sample(a_op, nq, step * r)
+        j0 = min(coarse.shape[1], int(math.ceil(4.0 * big_j / r)))
+        thr0 = _row_kth(coarse, None, j0, 0.0, 0)
+        cap_s = 1 << max(10, int(math.ceil(math.log2(16 * big_j))))
+        count, score, _ = self._filter(a_op, nq, thr0, cap_s, step=step)
+        return score, count, thr0
 
     def _rescore_select(self, q_raw, q_norm, nq, k, wts, excl, cand, bound, thr, eps, certify):
         """Exact fp64 rescore of the candidates above ``bound`` + local top-k (global row ids)."""
@@ -351,9 +359,10 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
     with the same queries).  All shards work against ONE per-query threshold:
 
     1. K1 on the query batch; the measured error bound ``eps`` (max over ranks).
-    2. K2 STORE over every ``step``-th row of each shard; the top-J sample scores of every shard are gathered and
-       the global threshold is ``max(kth(union, j) - 2 eps, kth(union, j_cap))`` -- what one GPU would compute on
-       the whole corpus, so each shard appends only its share of the candidates.
+    2. the largest scores of a ``step``-strided sample of each shard (a coarse K2 STORE pass sets a floor, a K2
+       FILTER pass over the sample keeps what exceeds it); the top-J of every shard are gathered and the global
+       threshold is ``max(kth(union, j) - 2 eps, kth(union, j_cap))`` -- what one GPU would compute on the whole
+       corpus, so each shard appends only its share of the candidates.
     3. K2 FILTER over each shard (the score matrix never reaches HBM).
     4. the kk-th largest approximate candidate score over all shards - 2 eps bounds what needs an exact score.
     5. exact fp64 rescore + local top-k per shard; ONE gather of the ``[nq, k]`` lists; merge (K3) with the
@@ -412,16 +421,37 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
     pl = plan(kk, n_total)
     live = [s for s in stores if s.n]
     # 2: one global threshold from the shards' samples
-    samples = [s._sample(a_op, nq, pl["step"]) for s in live]
-    if solo:
-        thr = _row_kth(samples[0], None, pl["j"], 2.0 * eps, pl["j_cap"])
+    big_j = max(pl["j"], pl["j_cap"])
+    if pl["n_sample"] >= 8192:
+        # two-level: the sample matrix (2.1 GB at 10 M rows) is never written or radix-selected
+        tops, floor = [], None
+        for s in live:
+            sc, cnt, thr0 = s._sample_top(a_op, nq, pl["step"], big_j)
+            tops.append((sc, cnt))
+            floor = thr0 if floor is None else torch.minimum(floor, thr0)
+        if solo:
+            thr = _row_kth(tops[0][0], tops[0][1], pl["j"], 2.0 * eps, pl["j_cap"])
+        else:
+            lists = [_row_topj(sc, cnt, big_j) for sc, cnt in tops]
+            if not lists:
+                lists = [torch.full((nq, big_j), float("-inf"), dtype=torch.float32, device=dev)]
+                floor = torch.full((nq,), float("-inf"), dtype=torch.float32, device=dev)
+            thr = _row_kth(_union(lists, comm), None, pl["j"], 2.0 * eps, pl["j_cap"])
+            floor = -comm.max_(-floor)                                   # min over the ranks
+        # a list that came out too short gives -inf (or a value below the floor): fall back to the coarse floor,
+        # which ~0.4 % of the corpus exceeds -- far more than k rows, so it is below the k-th best score
+        thr = torch.maximum(thr, floor - 2.0 * eps)
+        del tops
     else:
-        big_j = max(pl["j"], pl["j_cap"])
-        tops = [_row_topj(sm, None, big_j) for sm in samples]
-        if not tops:
-            tops = [torch.full((nq, big_j), float("-inf"), dtype=torch.float32, device=dev)]
-        thr = _row_kth(_union(tops, comm), None, pl["j"], 2.0 * eps, pl["j_cap"])
-    del samples
+        samples = [s._sample(a_op, nq, pl["step"]) for s in live]
+        if solo:
+            thr = _row_kth(samples[0], None, pl["j"], 2.0 * eps, pl["j_cap"])
+        else:
+            lists = [_row_topj(sm, None, big_j) for sm in samples]
+            if not lists:
+                lists = [torch.full((nq, big_j), float("-inf"), dtype=torch.float32, device=dev)]
+            thr = _row_kth(_union(lists, comm), None, pl["j"], 2.0 * eps, pl["j_cap"])
+        del samples
     ph.mark("sample_threshold")
     cap = pl["cap"] if solo else max(2048, min(pl["cap"], 1 << int(math.ceil(math.log2(4.0 * pl["cap"] / n_shards)))))
     n_shard_max = max(s.n for s in live) if live else 1

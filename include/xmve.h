@@ -97,13 +97,14 @@ XMVE_API int xmve_score_store(const void* a_op, int64_t nq, int64_t a_ld,
  *   s >  hi[q]            -> count_above[q] += 1                    (hi may be NULL = +inf)
  *   lo[q] < s <= hi[q]    -> slot = cand_count[q]++ ; if slot < cap:
  *                            cand_score[q*cap+slot] = s, cand_idx[q*cap+slot] = v
- * cand_count keeps counting past cap so the caller can detect overflow.  Replaces the full
+ * cand_count keeps counting past cap so the caller can detect overflow.  b_row_step as in xmve_score_store (v is
+ * then the index of the sampled row).  Replaces the full
  * argsort of every row (LINAS-engine/inference.py:79; MultiFusion/src/validate.py:74,92) as a
  * streaming threshold top-k, and the rank-of-ground-truth search (util/metrics.py:139-145) as
  * count_above with a guard band.
  */
 XMVE_API int xmve_score_filter(const void* a_op, int64_t nq, int64_t a_ld,
-                      const void* b_op, int64_t nv, int64_t b_ld, int k,
+                      const void* b_op, int64_t nv, int64_t b_ld, int64_t b_row_step, int k,
                       const float* lo, const float* hi,
                       int32_t* count_above, int32_t* cand_count,
                       float* cand_score, int32_t* cand_idx, int32_t cap, void* stream);

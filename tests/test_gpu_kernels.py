@@ -124,7 +124,7 @@ def test_score_filter_window(N, nq, nv, d, use_hi, tile, monkeypatch):
     cand_count = torch.zeros(nq, dtype=torch.int32, device="cuda")
     cand_score = torch.zeros((nq, cap), dtype=torch.float32, device="cuda")
     cand_idx = torch.full((nq, cap), -1, dtype=torch.int32, device="cuda")
-    N.call("xmve_score_filter", N.ptr(a), nq, a.stride(0), N.ptr(b), nv, b.stride(0), d if d % 64 == 0 else _rup(d, 64),
+    N.call("xmve_score_filter", N.ptr(a), nq, a.stride(0), N.ptr(b), nv, b.stride(0), 1, d if d % 64 == 0 else _rup(d, 64),
            N.ptr(lo), N.ptr(hi), N.ptr(cnt_above) if use_hi else None, N.ptr(cand_count), N.ptr(cand_score),
            N.ptr(cand_idx), cap, N.stream_ptr())
     torch.cuda.synchronize()
@@ -156,7 +156,7 @@ def test_score_filter_counts_past_cap(N):
     cand_count = torch.zeros(nq, dtype=torch.int32, device="cuda")
     cand_score = torch.zeros((nq, cap), dtype=torch.float32, device="cuda")
     cand_idx = torch.zeros((nq, cap), dtype=torch.int32, device="cuda")
-    N.call("xmve_score_filter", N.ptr(a), nq, a.stride(0), N.ptr(b), nv, b.stride(0), 64, N.ptr(lo), None, None,
+    N.call("xmve_score_filter", N.ptr(a), nq, a.stride(0), N.ptr(b), nv, b.stride(0), 1, 64, N.ptr(lo), None, None,
            N.ptr(cand_count), N.ptr(cand_score), N.ptr(cand_idx), cap, N.stream_ptr())
     assert (cand_count == nv).all()                         # every (in-range) column counted, none of the padding
 

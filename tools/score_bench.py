@@ -86,7 +86,7 @@ def main():
 
         def run():
             cc.zero_()
-            N.call("xmve_score_filter", N.ptr(a), args.nq, a.stride(0), N.ptr(b), args.nv, b.stride(0), args.k, N.ptr(lo),
+            N.call("xmve_score_filter", N.ptr(a), args.nq, a.stride(0), N.ptr(b), args.nv, b.stride(0), 1, args.k, N.ptr(lo),
                    None, None, N.ptr(cc), N.ptr(cs), N.ptr(ci), cap, N.stream_ptr())
         for _ in range(3):
             run()

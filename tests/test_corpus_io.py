@@ -91,3 +91,45 @@ def test_video_data_pt_to_store(tmp_path):
     err = linas.cal_error(V, q)
     np.testing.assert_array_equal(i.cpu().numpy(), np.argsort(err, axis=1, kind="stable")[:, :5])
     np.testing.assert_allclose(s.cpu().numpy(), -np.sort(err, axis=1)[:, :5], rtol=0, atol=1e-12)
+
+
+def test_cli_arguments():
+    from cross_modal_video_engine_b200 import cli
+    a = cli.parse_args(["search", "--corpus", "c", "--queries", "q.npy", "--dims", "1536,512", "--weights", "0.6,0.4"])
+    assert a.cmd == "search" and a.dims == (1536, 512) and a.weights == (0.6, 0.4) and a.topK == 10
+    with pytest.raises(SystemExit):
+        cli.parse_args(["search", "--corpus", "c", "--queries", "q.npy", "--dims", "8,8", "--weights", "1"])
+    with pytest.raises(SystemExit):
+        cli.parse_args(["eval", "--corpus", "c", "--queries", "q.npy"])          # --caption-ids is required
+
+
+@pytest.mark.gpu
+def test_cli_search_and_eval(tmp_path, capsys):
+    """inference.py's tail (ids of the top-K) and tester.py's tail (cal_perf log lines) on files."""
+    from cross_modal_video_engine_b200 import cli, synth
+    from oracle import linas
+    V, Q, vid, cap, _ = synth.msrvtt_like(91, 400, 3, 64, 2.0)
+    corpus_io.write_bigfile(str(tmp_path / "bf"), vid, V)
+    np.save(str(tmp_path / "q.npy"), Q)
+    (tmp_path / "cap.txt").write_text(" ".join(cap))
+    assert cli.main(["search", "--corpus", str(tmp_path / "bf"), "--queries", str(tmp_path / "q.npy"), "--topK", "5"]) == 0
+    lines = capsys.readouterr().out.strip().splitlines()
+    err = linas.cal_error(V.astype(np.float64), Q.astype(np.float64))
+    assert len(lines) == len(Q)
+    for r in (0, 7, len(Q) - 1):
+        assert lines[r] == str([vid[i] for i in np.argsort(err[r], kind="stable")[:5]])
+    run = tmp_path / "run.trec"
+    cli.main(["search", "--corpus", str(tmp_path / "bf"), "--queries", str(tmp_path / "q.npy"), "--topK", "3",
+              "--run-file", str(run)])
+    first = run.read_text().splitlines()[0].split()
+    assert first[:2] == ["q0", "Q0"] and first[2] == vid[int(np.argmin(err[0]))] and first[3] == "1"
+    capsys.readouterr()
+    cli.main(["eval", "--corpus", str(tmp_path / "bf"), "--queries", str(tmp_path / "q.npy"), "--caption-ids",
+              str(tmp_path / "cap.txt"), "--save-topk", str(tmp_path / "topk.pt")])
+    out = capsys.readouterr().out
+    ref = linas.cal_perf(err, *linas.get_gt(vid, cap))
+    for tup in ref:                                                              # validate.py:25-35: both directions
+        assert " * r_1_5_10, medr, meanr: {}".format([round(x, 1) for x in tup[:5]]) in out
+        assert " * mAP: {}".format(round(tup[5], 4)) in out
+    saved = torch.load(str(tmp_path / "topk.pt"), weights_only=False)
+    assert saved["idx"].shape == (len(Q), 10) and saved["video_ids"] == vid

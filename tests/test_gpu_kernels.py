@@ -37,7 +37,8 @@ def _operands(N, nq, nv, d, seed, layout_q=0, layout_v=0):
 
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,d,frames,dtype", [(1000, 1536, 1, torch.float32), (77, 100, 1, torch.float64),
-                                              (300, 640, 8, torch.float32), (5, 2048, 1, torch.float32)])
+                                              (300, 640, 8, torch.float32), (5, 2048, 1, torch.float32),
+                                              (130, 3000, 1, torch.float32), (64, 513, 2, torch.float32)])
 def test_prepare_rows(N, n, d, frames, dtype):
     g = torch.Generator(device="cuda").manual_seed(1)
     shape = (n, d) if frames == 1 else (n, frames, d)
@@ -67,7 +68,8 @@ def test_prepare_rows(N, n, d, frames, dtype):
     # measured quantisation residual of the hi plane: || 0.5 * x_hat - bf16(0.5 * x_hat) ||^2, rounded up
     exact = 0.5 * (raw[:, 4:4 + d].double() / nrm[:, None])
     ref_res = ((exact - hi.double()) ** 2).sum(1)
-    assert torch.all(res.double() >= ref_res * (1 - 1e-6)) and torch.all(res.double() <= ref_res * (1 + 1e-5) + 1e-30)
+    # an upper bound by contract: exact on the generic path, inflated by 1e-3 on the register-resident fp32 path
+    assert torch.all(res.double() >= ref_res * (1 - 1e-6)) and torch.all(res.double() <= ref_res * 1.0011 + 1e-30)
     assert torch.all(res.double().sqrt() <= 0.5 * 2.0 ** -8 * 1.0001)      # never above the worst-case rounding bound
 
 

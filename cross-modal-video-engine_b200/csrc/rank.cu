@@ -14,50 +14,61 @@
 namespace xmve {
 namespace {
 
-constexpr int GT_GROUP = 8;      // ground-truth items ranked per pass over the data
-
-// axis 0: query = row i.  One block per (row, group of GT_GROUP ground-truth entries).
-template <typename T>
+// axis 0: query = row i.  One WARP per (row, group of G ground-truth entries): lanes stride over the row with four
+// independent loads in flight, so a 24 KB row of doubles is read at memory speed (a block per row with a dozen
+// elements per thread was latency-bound: 1.3 TB/s at the MSR-VTT full-test shape).
+template <typename T, int G>
 __global__ void __launch_bounds__(256)
-gt_ranks_rows_kernel(const T* __restrict__ x, int64_t n_col, int64_t ld, const int64_t* __restrict__ gt_off,
-                     const int32_t* __restrict__ gt_ids, int32_t* __restrict__ ranks) {
-  const int64_t q = blockIdx.x;
-  const int64_t e0 = gt_off[q] + static_cast<int64_t>(blockIdx.y) * GT_GROUP;
-  const int64_t e1 = min(gt_off[q + 1], e0 + GT_GROUP);
+gt_ranks_rows_kernel(const T* __restrict__ x, int64_t n_query, int64_t n_col, int64_t ld, int n_groups,
+                     const int64_t* __restrict__ gt_off, const int32_t* __restrict__ gt_ids,
+                     int32_t* __restrict__ ranks) {
+  const int lane = threadIdx.x & 31;
+  const int64_t unit = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int64_t q = unit / n_groups;
+  if (q >= n_query) return;
+  const int64_t e0 = gt_off[q] + (unit - q * n_groups) * G;
+  const int64_t e1 = min(gt_off[q + 1], e0 + G);
   if (e0 >= e1) return;
   const int ng = static_cast<int>(e1 - e0);
   const T* __restrict__ row = x + q * ld;
-  __shared__ int s_cnt[GT_GROUP];
-  T gv[GT_GROUP];
-  int gi[GT_GROUP], cnt[GT_GROUP];
+  T gv[G];
+  int gi[G], cnt[G];
 #pragma unroll
-  for (int g = 0; g < GT_GROUP; ++g) {
+  for (int g = 0; g < G; ++g) {
     gi[g] = g < ng ? gt_ids[e0 + g] : 0;
     gv[g] = row[gi[g]];
     cnt[g] = 0;
   }
-  if (threadIdx.x < GT_GROUP) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  for (int64_t m = threadIdx.x; m < n_col; m += blockDim.x) {
+  int64_t m = lane;
+  for (; m + 96 < n_col; m += 128) {
+    const T v0 = row[m], v1 = row[m + 32], v2 = row[m + 64], v3 = row[m + 96];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      cnt[g] += (v0 < gv[g] || (v0 == gv[g] && m < gi[g])) ? 1 : 0;
+      cnt[g] += (v1 < gv[g] || (v1 == gv[g] && m + 32 < gi[g])) ? 1 : 0;
+      cnt[g] += (v2 < gv[g] || (v2 == gv[g] && m + 64 < gi[g])) ? 1 : 0;
+      cnt[g] += (v3 < gv[g] || (v3 == gv[g] && m + 96 < gi[g])) ? 1 : 0;
+    }
+  }
+  for (; m < n_col; m += 32) {
     const T v = row[m];
 #pragma unroll
-    for (int g = 0; g < GT_GROUP; ++g) cnt[g] += (v < gv[g] || (v == gv[g] && m < gi[g])) ? 1 : 0;
+    for (int g = 0; g < G; ++g) cnt[g] += (v < gv[g] || (v == gv[g] && m < gi[g])) ? 1 : 0;
   }
 #pragma unroll
-  for (int g = 0; g < GT_GROUP; ++g) {
+  for (int g = 0; g < G; ++g) {
     int c = cnt[g];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && g < ng) atomicAdd(&s_cnt[g], c);
+    if (lane == 0 && g < ng) ranks[e0 + g] = 1 + c;
   }
-  __syncthreads();
-  if (threadIdx.x < ng) ranks[e0 + threadIdx.x] = 1 + s_cnt[threadIdx.x];
 }
 
 // axis 1: query = column i, memories = rows.  A block owns 32 adjacent columns (lane <-> column, so
 // every row read is one coalesced line) and a slice of the rows; partial counts are added atomically
-// into ranks[] (zeroed by the host wrapper; slice 0 adds the leading 1).
-template <typename T>
+// into ranks[] (zeroed by the host wrapper; slice 0 adds the leading 1).  G ground-truth entries are ranked per
+// pass over the data: G = 24 covers the 20 captions per video of MSR-VTT in ONE pass.
+template <typename T, int G>
 __global__ void __launch_bounds__(256)
 gt_ranks_cols_kernel(const T* __restrict__ x, int64_t n_row, int64_t n_col, int64_t ld,
                      const int64_t* __restrict__ gt_off, const int32_t* __restrict__ gt_ids, int max_gt,
@@ -68,25 +79,34 @@ gt_ranks_cols_kernel(const T* __restrict__ x, int64_t n_row, int64_t n_col, int6
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_slice;
   const int64_t r1 = min(n_row, r0 + rows_per_slice);
   const int64_t e_lo = col_ok ? gt_off[col] : 0, e_hi = col_ok ? gt_off[col + 1] : 0;
-  for (int base = 0; base < max_gt; base += GT_GROUP) {
-    T gv[GT_GROUP];
-    int gi[GT_GROUP], cnt[GT_GROUP];
+  for (int base = 0; base < max_gt; base += G) {
+    T gv[G];
+    int gi[G], cnt[G];
 #pragma unroll
-    for (int g = 0; g < GT_GROUP; ++g) {
+    for (int g = 0; g < G; ++g) {
       const bool ok = e_lo + base + g < e_hi;
       gi[g] = ok ? gt_ids[e_lo + base + g] : -1;
       gv[g] = ok ? x[static_cast<int64_t>(gi[g]) * ld + col] : static_cast<T>(0);
       cnt[g] = 0;
     }
     if (col_ok) {
-      for (int64_t m = r0 + warp; m < r1; m += 8) {
+      int64_t m = r0 + warp;
+      for (; m + 8 < r1; m += 16) {                              // two independent row reads in flight
+        const T va = x[m * ld + col], vb = x[(m + 8) * ld + col];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          cnt[g] += (va < gv[g] || (va == gv[g] && m < gi[g])) ? 1 : 0;
+          cnt[g] += (vb < gv[g] || (vb == gv[g] && m + 8 < gi[g])) ? 1 : 0;
+        }
+      }
+      for (; m < r1; m += 8) {
         const T v = x[m * ld + col];
 #pragma unroll
-        for (int g = 0; g < GT_GROUP; ++g) cnt[g] += (v < gv[g] || (v == gv[g] && m < gi[g])) ? 1 : 0;
+        for (int g = 0; g < G; ++g) cnt[g] += (v < gv[g] || (v == gv[g] && m < gi[g])) ? 1 : 0;
       }
     }
 #pragma unroll
-    for (int g = 0; g < GT_GROUP; ++g) {
+    for (int g = 0; g < G; ++g) {
       if (gi[g] >= 0) {
         const int add = cnt[g] + ((blockIdx.y == 0 && warp == 0) ? 1 : 0);
         if (add != 0) atomicAdd(&ranks[e_lo + base + g], add);
@@ -216,27 +236,32 @@ extern "C" int xmve_gt_ranks(const void* errors, int dtype, int64_t n_row, int64
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n_entries == 0 || max_gt == 0) return XMVE_OK;
   if (axis == 0) {
-    dim3 grid(static_cast<unsigned>(n_query), static_cast<unsigned>((max_gt + GT_GROUP - 1) / GT_GROUP));
-    if (grid.y > 65535) return fail(XMVE_ERR_LIMIT, "gt_ranks: too many ground-truth entries per query");
-    if (dtype == XMVE_F32)
-      gt_ranks_rows_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(errors), n_col, ld, gt_off, gt_ids, ranks);
-    else
-      gt_ranks_rows_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(errors), n_col, ld, gt_off, gt_ids, ranks);
+    const int G = max_gt == 1 ? 1 : 8;
+    const int n_groups = (max_gt + G - 1) / G;
+    const int64_t units = n_query * n_groups;
+    const unsigned grid = static_cast<unsigned>((units + 7) / 8);
+    if ((units + 7) / 8 > 2147483647LL) return fail(XMVE_ERR_LIMIT, "gt_ranks: too many (query, ground-truth) units");
+#define XMVE_ROWS(T, GG)                                                                                          \
+  gt_ranks_rows_kernel<T, GG><<<grid, 256, 0, st>>>(static_cast<const T*>(errors), n_query, n_col, ld, n_groups, gt_off, \
+                                                    gt_ids, ranks)
+    if (dtype == XMVE_F32) { if (G == 1) XMVE_ROWS(float, 1); else XMVE_ROWS(float, 8); }
+    else { if (G == 1) XMVE_ROWS(double, 1); else XMVE_ROWS(double, 8); }
+#undef XMVE_ROWS
   } else {
     XMVE_CUDA(cudaMemsetAsync(ranks, 0, static_cast<size_t>(n_entries) * sizeof(int32_t), st));
     const int col_blocks = static_cast<int>((n_col + 31) / 32);
     int slices = (4 * sm_count() + col_blocks - 1) / col_blocks;
     if (slices < 1) slices = 1;
     int rows_per_slice = static_cast<int>((n_row + slices - 1) / slices);
-    rows_per_slice = (rows_per_slice + 7) / 8 * 8;
+    rows_per_slice = (rows_per_slice + 15) / 16 * 16;
     slices = static_cast<int>((n_row + rows_per_slice - 1) / rows_per_slice);
     dim3 grid(static_cast<unsigned>(col_blocks), static_cast<unsigned>(slices));
-    if (dtype == XMVE_F32)
-      gt_ranks_cols_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(errors), n_row, n_col, ld, gt_off,
-                                                        gt_ids, max_gt, rows_per_slice, ranks);
-    else
-      gt_ranks_cols_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(errors), n_row, n_col, ld, gt_off,
-                                                         gt_ids, max_gt, rows_per_slice, ranks);
+#define XMVE_COLS(T, GG)                                                                                          \
+  gt_ranks_cols_kernel<T, GG><<<grid, 256, 0, st>>>(static_cast<const T*>(errors), n_row, n_col, ld, gt_off, gt_ids,   \
+                                                    max_gt, rows_per_slice, ranks)
+    if (dtype == XMVE_F32) { if (max_gt <= 8) XMVE_COLS(float, 8); else XMVE_COLS(float, 24); }
+    else { if (max_gt <= 8) XMVE_COLS(double, 8); else XMVE_COLS(double, 24); }
+#undef XMVE_COLS
   }
   return launch_status("gt_ranks kernel");
 }

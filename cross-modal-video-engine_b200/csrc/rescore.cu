@@ -123,46 +123,77 @@ rescore_kernel(const float* __restrict__ q_raw, int64_t nq, int64_t q_ld, const 
 }
 
 // ---- tiled fp64 score matrix: out = alpha * A * B^T ----------------------------------------------
-constexpr int TM = 64, TN = 64, TK = 16;   // 256 threads, 4 x 4 outputs each
+// 128 x 64 output tile, 256 threads with 8 x 4 outputs each (32 DFMA per 6 shared-memory loads of 16 bytes), the next
+// k-slab is fetched into registers while the current one is multiplied.
+constexpr int TM = 128, TN = 64, TK = 16;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 score_f64_kernel(const double* __restrict__ a, int64_t nq, int64_t a_ld, const double* __restrict__ b, int64_t nv,
                  int64_t b_ld, int k, double alpha, double* __restrict__ out, int64_t out_ld) {
-  __shared__ double as[TK][TM + 1];
-  __shared__ double bs[TK][TN + 1];
+  __shared__ __align__(16) double as[TK][TM + 2];
+  __shared__ __align__(16) double bs[TK][TN + 2];
   const int64_t q0 = static_cast<int64_t>(blockIdx.y) * TM, v0 = static_cast<int64_t>(blockIdx.x) * TN;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  double acc[4][4] = {};
-  for (int k0 = 0; k0 < k; k0 += TK) {
-    for (int e = threadIdx.x; e < TM * TK; e += 256) {
-      const int r = e / TK, c = e % TK;
-      as[c][r] = (q0 + r < nq && k0 + c < k) ? a[(q0 + r) * a_ld + k0 + c] : 0.0;
-      bs[c][r] = (v0 + r < nv && k0 + c < k) ? b[(v0 + r) * b_ld + k0 + c] : 0.0;
-    }
-    __syncthreads();
+  // global -> registers: A slab 128 x 16 (8 doubles per thread), B slab 64 x 16 (4 per thread); k fastest
+  const int lr = threadIdx.x >> 2, lc = (threadIdx.x & 3) * 4;         // row 0..63, k offset 0,4,8,12
+  double ra[2][4], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int c = 0; c < TK; ++c) {
-      double av[4], bv[4];
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        av[i] = as[c][ty * 4 + i];
-        bv[i] = bs[c][tx * 4 + i];
+      for (int e = 0; e < 4; ++e) {
+        const int64_t r = q0 + lr + 64 * h;
+        ra[h][e] = (r < nq && k0 + lc + e < k) ? a[r * a_ld + k0 + lc + e] : 0.0;
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+    for (int e = 0; e < 4; ++e) {
+      const int64_t r = v0 + lr;
+      rb[e] = (r < nv && k0 + lc + e < k) ? b[r * b_ld + k0 + lc + e] : 0.0;
+    }
+  };
+  double acc[8][4] = {};
+  fetch(0);
+  for (int k0 = 0; k0 < k; k0 += TK) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      as[lc + e][lr] = ra[0][e];
+      as[lc + e][lr + 64] = ra[1][e];
+      bs[lc + e][lr] = rb[e];
+    }
+    __syncthreads();
+    if (k0 + TK < k) fetch(k0 + TK);                                    // in flight during the multiply
+#pragma unroll
+    for (int c = 0; c < TK; ++c) {
+      double av[8], bv[4];
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        const double2 t = *reinterpret_cast<const double2*>(&as[c][ty * 8 + i]);
+        av[i] = t.x;
+        av[i + 1] = t.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j += 2) {
+        const double2 t = *reinterpret_cast<const double2*>(&bs[c][tx * 4 + j]);
+        bv[j] = t.x;
+        bv[j + 1] = t.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int64_t q = q0 + ty * 4 + i, v = v0 + tx * 4 + j;
+      const int64_t q = q0 + ty * 8 + i, v = v0 + tx * 4 + j;
       if (q < nq && v < nv) out[q * out_ld + v] = alpha * acc[i][j];
     }
 }
+
+constexpr int PTM = 64, PTN = 64, PTK = 16;   // pairwise measures: 256 threads, 4 x 4 outputs each
 
 // ---- non-cosine measures of cal_error (evaluation.py:22-35): tiled pairwise distances on the CUDA cores --------
 // out[q, v] = alpha * f(a_q, b_v) + beta with f = sum|a-b| (L1), sqrt(sum (a-b)^2) (L2) or sum min / sum max (jaccard).
@@ -170,21 +201,21 @@ template <int MEASURE>
 __global__ void __launch_bounds__(256)
 pairwise_kernel(const double* __restrict__ a, int64_t nq, int64_t a_ld, const double* __restrict__ b, int64_t nv,
                 int64_t b_ld, int k, double alpha, double beta, double* __restrict__ out, int64_t out_ld) {
-  __shared__ double as[TK][TM + 1];
-  __shared__ double bs[TK][TN + 1];
-  const int64_t q0 = static_cast<int64_t>(blockIdx.y) * TM, v0 = static_cast<int64_t>(blockIdx.x) * TN;
+  __shared__ double as[PTK][PTM + 1];
+  __shared__ double bs[PTK][PTN + 1];
+  const int64_t q0 = static_cast<int64_t>(blockIdx.y) * PTM, v0 = static_cast<int64_t>(blockIdx.x) * PTN;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   double acc[4][4] = {};
   double acc2[MEASURE == XMVE_MEASURE_JACCARD ? 4 : 1][4] = {};
-  for (int k0 = 0; k0 < k; k0 += TK) {
-    for (int e = threadIdx.x; e < TM * TK; e += 256) {
-      const int r = e / TK, c = e % TK;
+  for (int k0 = 0; k0 < k; k0 += PTK) {
+    for (int e = threadIdx.x; e < PTM * PTK; e += 256) {
+      const int r = e / PTK, c = e % PTK;
       as[c][r] = (q0 + r < nq && k0 + c < k) ? a[(q0 + r) * a_ld + k0 + c] : 0.0;
       bs[c][r] = (v0 + r < nv && k0 + c < k) ? b[(v0 + r) * b_ld + k0 + c] : 0.0;
     }
     __syncthreads();
 #pragma unroll
-    for (int c = 0; c < TK; ++c) {
+    for (int c = 0; c < PTK; ++c) {
       double av[4], bv[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -234,8 +265,8 @@ extern "C" int xmve_pairwise_f64(const double* a, int64_t nq, int64_t a_ld, cons
                "pairwise_f64: bad arguments");
   XMVE_REQUIRE(measure >= XMVE_MEASURE_L1 && measure <= XMVE_MEASURE_JACCARD, "pairwise_f64: unknown measure %d", measure);
   if (nq == 0 || nv == 0) return XMVE_OK;
-  dim3 grid(static_cast<unsigned>((nv + TN - 1) / TN), static_cast<unsigned>((nq + TM - 1) / TM));
-  if (grid.y > 65535) return fail(XMVE_ERR_LIMIT, "pairwise_f64: more than %d query rows; chunk the call", 65535 * TM);
+  dim3 grid(static_cast<unsigned>((nv + PTN - 1) / PTN), static_cast<unsigned>((nq + PTM - 1) / PTM));
+  if (grid.y > 65535) return fail(XMVE_ERR_LIMIT, "pairwise_f64: more than %d query rows; chunk the call", 65535 * PTM);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (measure == XMVE_MEASURE_L1)
     pairwise_kernel<XMVE_MEASURE_L1><<<grid, 256, 0, st>>>(a, nq, a_ld, b, nv, b_ld, k, alpha, beta, out, out_ld);

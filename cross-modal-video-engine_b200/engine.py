@@ -542,6 +542,35 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
     return out_s, out_i
 
 
+def search_norm_score(stores, queries, k, weights=None, comm=None, n_total=None, **kw):
+    """Top-``k`` under ``norm_score`` fusion: every space's score matrix is
+    min-max normalised over the WHOLE matrix (LINAS-engine/validate.py:7-11) before the weighted sum,
+    ``fused[q, v] = sum_s w_s * (cos_s[q, v] - min_s) / (max_s - min_s)``.
+
+    For corpora whose matrices cannot exist this is an affine map of the cosines, so the ranking equals that of a
+    weighted-cosine search with ``w_s / (max_s - min_s)``; the global extremes are exact: ``max_s`` is the largest
+    top-1 score of a one-hot search of space s, ``min_s`` minus the largest top-1 score of the negated queries.
+    Costs ``2 S`` extra top-1 searches.  Returns ``(fused scores fp64 [nq, k], idx)``; the errors the reference
+    would rank are ``-fused``."""
+    stores = list(stores) if isinstance(stores, (list, tuple)) else [stores]
+    ref = stores[0]
+    n_space = len(ref.dims)
+    wts = _weights(weights, n_space)
+    q_dev = [_to_device(x, ref.device) for x in _as_spaces(queries, ref.dims)]
+    q_all = q_dev[0] if n_space == 1 else torch.cat(q_dev, dim=-1)
+    adj, shift = [], 0.0
+    for s in range(n_space):
+        onehot = [1.0 if t == s else 0.0 for t in range(n_space)]
+        top, _ = search_shards(stores, q_all, 1, weights=onehot, comm=comm, n_total=n_total, **kw)
+        bot, _ = search_shards(stores, -q_all, 1, weights=onehot, comm=comm, n_total=n_total, **kw)
+        hi, lo = float(top.max()), -float(bot.max())            # global extremes of cos_s over all (q, v)
+        rng = hi - lo                                            # s / np.max(s) after s -= np.min(s)
+        adj.append(wts[s] / rng)
+        shift += wts[s] * lo / rng
+    scores, idx = search_shards(stores, q_all, k, weights=adj, comm=comm, n_total=n_total, **kw)
+    return scores - shift, idx
+
+
 def _merge(scores, idx, k, thr=None, eps=0.0, overflow=None):
     """K3 on ``[nq, m]`` (score, global index) pairs -> top-``k`` (+ certificate when ``thr`` is given)."""
     nq, m = scores.shape

@@ -249,6 +249,21 @@ def test_eval_q2m_from_topk_lists(X):
     assert n_found < len(Q) and np.isnan(meanr)                 # some captions rank beyond the lists
 
 
+def test_search_under_norm_score_fusion(X):
+    """norm_score fusion at a size that takes the filter path: same top-k as the oracle's
+    sum_s w_s * norm_score(cal_error_s) matrix, fused scores within 1e-12."""
+    dims, w = (128, 64), (0.6, 0.4)
+    nv, nq, k = 40000, 50, 20
+    V, Q = X.synth.clustered(91, nv, sum(dims), n_centroid=300), X.synth.clustered(92, nq, sum(dims), n_centroid=300)
+    store = X.engine.CorpusStore(nv, dims).add(torch.from_numpy(V))
+    s, i = X.engine.search_norm_score(store, torch.from_numpy(Q), k, weights=w)
+    V64, Q64 = V.astype(np.float64), Q.astype(np.float64)
+    err = linas.fused_errors([V64[:, :128], V64[:, 128:]], [Q64[:, :128], Q64[:, 128:]], w, mode="norm_score")
+    ref = np.argsort(err, axis=1, kind="stable")[:, :k]
+    np.testing.assert_array_equal(i.cpu().numpy(), ref)
+    np.testing.assert_allclose(s.cpu().numpy(), -np.take_along_axis(err, ref, axis=1), rtol=0, atol=1e-12)
+
+
 def test_search_exact_ties_are_ordered_by_index(X):
     """Every corpus vector appears three times: the top-k is full of exact score ties, also across the k boundary.
     Engine order = (score desc, index asc) = what a stable argsort of the reference's error row gives."""

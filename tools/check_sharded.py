@@ -1,0 +1,61 @@
+"""Multi-GPU correctness check (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_sharded.py
+
+Every rank holds one shard of a seeded corpus; ``distributed.sharded_search`` over NCCL must return, on every rank,
+exactly what ONE store holding the whole corpus returns (indices identical, fp64 scores identical), with and
+without exclusions, for the filtered path and the small-corpus path, plus ``upload_rows`` and the AVS AP.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cross_modal_video_engine_b200 import avs, distributed, engine, synth  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    dims, w = (256, 64), (0.7, 0.3)
+    ok = True
+    for nv, nq, k in ((600_000, 300, 100), (9_000, 64, 10), (300_001, 7, 1000)):
+        V = synth.device_gaussian(nv, sum(dims), 11, dev)             # same seed on every rank -> same corpus
+        Q = synth.device_gaussian(nq, sum(dims), 12, dev)
+        lo, hi = distributed.shard_range(nv, world, rank)
+        shard = engine.CorpusStore(hi - lo, dims, device=dev, index_offset=lo).add(V[lo:hi])
+        full = engine.CorpusStore(nv, dims, device=dev).add(V)
+        excl = torch.randint(0, nv, (nq,), generator=torch.Generator().manual_seed(5)).numpy()
+        for ex in (None, excl):
+            s_ref, i_ref = full.search(Q, k, weights=w, exclude=ex)
+            s, i = distributed.sharded_search(shard, Q, k, weights=w, exclude=ex, n_total=nv)
+            same = bool(torch.equal(i, i_ref)) and bool(torch.equal(s, s_ref))
+            ok = ok and same
+            if rank == 0:
+                print("nv=%d nq=%d k=%d exclude=%s: %s" % (nv, nq, k, ex is not None, "identical" if same else "MISMATCH"),
+                      flush=True)
+        if k == 1000:
+            rel = [sorted(set(np.random.default_rng(q).integers(0, nv, 300).tolist())) for q in range(nq)]
+            s, i = avs.search_avs(shard, Q, k, weights=w, comm=distributed.GroupComm(), n_total=nv)
+            ap, m = avs.ap_at_k(i, rel, nv, k)
+            ap_ref, m_ref = avs.ap_at_k(full.search(Q, k, weights=w)[1], rel, nv, k)
+            ok = ok and bool((ap == ap_ref).all()) and m == m_ref
+        del shard, full, V
+        torch.cuda.empty_cache()
+    host = torch.arange(1000 * 8, dtype=torch.float32).reshape(1000, 8).pin_memory()
+    ok = ok and bool(torch.equal(distributed.upload_rows(host, device=dev).cpu(), host))
+    t = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("sharded search on %d GPUs: %s" % (world, "OK" if int(t) == 1 else "FAILED"), flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if int(t) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

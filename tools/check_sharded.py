@@ -47,6 +47,36 @@ def main():
             ok = ok and bool((ap == ap_ref).all()) and m == m_ref
         del shard, full, V
         torch.cuda.empty_cache()
+    # the re-run loop in lockstep on every rank: (a) near-duplicates on the sampling grid -> first threshold too high,
+    # (b) dense neighbourhoods -> candidate lists overflow and must grow
+    nv, nq, d, k = 200_000, 64, 128, 50
+    g = torch.Generator(device=dev).manual_seed(21)
+    for case in ("grid", "dense"):
+        V = torch.randn((nv, d), generator=g, device=dev)
+        Q = torch.randn((nq, d), generator=g, device=dev)
+        if case == "grid":
+            step = engine.plan(k, nv)["step"]
+            grid = torch.arange(0, nv, step, device=dev)
+            grid = grid[torch.randperm(grid.numel(), generator=g, device=dev)][: 30 * nq].reshape(nq, 30)
+            for qi in range(nq):
+                V[grid[qi]] = Q[qi] + 0.3 * torch.randn((30, d), generator=g, device=dev)
+        else:
+            for qi in range(4):
+                rows = torch.randperm(nv, generator=g, device=dev)[:30000]
+                V[rows] = Q[qi] * 2.0 + 0.4 * torch.randn((30000, d), generator=g, device=dev)
+        lo, hi = distributed.shard_range(nv, world, rank)
+        shard = engine.CorpusStore(hi - lo, (d,), device=dev, index_offset=lo).add(V[lo:hi])
+        full = engine.CorpusStore(nv, (d,), device=dev).add(V)
+        st = {}
+        s_ref, i_ref = full.search(Q, k)
+        s, i = distributed.sharded_search(shard, Q, k, n_total=nv, stats=st)
+        same = bool(torch.equal(i, i_ref)) and bool(torch.equal(s, s_ref))
+        ok = ok and same and st.get("reruns", 0) >= 1
+        if rank == 0:
+            print("re-run case %-5s: %s, %d re-run pass(es), %d row(s)" % (case, "identical" if same else "MISMATCH",
+                                                                       st.get("reruns", 0), st.get("rerun_rows", 0)), flush=True)
+        del shard, full, V
+        torch.cuda.empty_cache()
     host = torch.arange(1000 * 8, dtype=torch.float32).reshape(1000, 8).pin_memory()
     ok = ok and bool(torch.equal(distributed.upload_rows(host, device=dev).cpu(), host))
     t = torch.tensor([1 if ok else 0], device=dev)

@@ -383,7 +383,7 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
     if n_total == 0:
         raise ValueError("empty corpus")
     wts = _weights(weights, n_space)
-    ph = _Phases(stats is not None)
+    ph = _Phases(stats is not None and ref.device.type == "cuda")
     ph.mark("start")
     a_op, q_raw, q_norm, q_res, nq = ref.prepare_queries(queries, wts)
     ph.mark("prepare_queries")

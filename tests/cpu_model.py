@@ -1,0 +1,189 @@
+"""A CPU *model* of one corpus shard for protocol tests (test infrastructure, never shipped).
+
+``engine.search_shards`` orchestrates kernels through a handful of shard-local methods and three module helpers.
+``ModelShard`` restates those methods in torch-CPU arithmetic (bf16-rounded operands and fp32 scores for the
+filter, fp64 for the rescore) and :func:`patch_engine` swaps the three helpers, so that the control flow of the
+multi-rank pipeline -- the global threshold, the gathered rescore bound, the certified merge and the re-run loop in
+lockstep -- runs under the ``gloo`` backend without a GPU.  The kernels themselves are tested on the B200.
+"""
+import math
+
+import torch
+
+
+def _sorted_topk(score, idx, k, exclude=None, idx_offset=0):
+    """(score desc, index asc) top-k of one row's valid entries -> (scores [k], ids [k], n_valid)."""
+    keep = score > float("-inf")
+    if exclude is not None and exclude >= 0:
+        keep &= (idx + idx_offset) != exclude
+    s, i = score[keep], idx[keep] + idx_offset
+    order = torch.argsort(i, stable=True)
+    s, i = s[order], i[order]
+    order = torch.argsort(s, descending=True, stable=True)[:k]
+    out_s = torch.full((k,), float("-inf"), dtype=torch.float64)
+    out_i = torch.full((k,), -1, dtype=torch.int64)
+    out_s[: len(order)], out_i[: len(order)] = s[order], i[order]
+    return out_s, out_i, int(keep.sum())
+
+
+def _certify(kth, n_valid, k, thr, eps, overflow, bound):
+    enough = n_valid >= k
+    complete = thr == float("-inf") or (kth - eps >= thr)
+    cert = int((not overflow) and enough and complete)
+    if overflow:
+        nxt = bound if bound is not None else thr
+    elif enough:
+        nxt = float(torch.tensor(kth, dtype=torch.float32)) - 1.0001 * eps - 1e-7
+    else:
+        nxt = thr - max(8.0 * eps, 0.25 * abs(thr))
+    return cert, nxt
+
+
+class ModelShard:
+    def __init__(self, rows, dims, index_offset=0):
+        self.dims, self.index_offset = tuple(dims), int(index_offset)
+        self.device = torch.device("cpu")
+        self.raw = rows.float()
+        self.n = rows.shape[0]
+        self.k = sum(dims)
+        parts, o = [], 0
+        self.norm = []
+        for d in dims:
+            x = self.raw[:, o:o + d].double()
+            nrm = torch.linalg.vector_norm(x, dim=1)
+            self.norm.append(nrm)
+            parts.append((x / nrm[:, None]).float().bfloat16().float())
+            o += d
+        self.op = torch.cat(parts, dim=1) if self.n else torch.zeros((0, self.k))
+        self._exact_unit = None
+
+    # -- what search_shards calls ---------------------------------------------------------------------
+    def prepare_queries(self, queries, wts):
+        q = torch.as_tensor(queries).float()
+        parts, res, norms, o = [], [], [], 0
+        for w, d in zip(wts, self.dims):
+            x = q[:, o:o + d].double()
+            nrm = torch.linalg.vector_norm(x, dim=1)
+            y = (w * (x / nrm[:, None]).float())
+            yb = y.bfloat16().float()
+            parts.append(yb)
+            res.append(((y - yb) ** 2).sum(1))
+            norms.append(nrm)
+            o += d
+        return torch.cat(parts, 1), q, torch.stack(norms), torch.stack(res).float(), q.shape[0]
+
+    def resid_max2(self):
+        o, tot = 0, torch.zeros(max(self.n, 1), dtype=torch.float64)
+        for d, nrm in zip(self.dims, self.norm):
+            y = (self.raw[:, o:o + d].double() / nrm[:, None]).float()
+            tot[: self.n] += ((y - y.bfloat16().float()) ** 2).sum(1).double()
+            o += d
+        return tot.max().float()
+
+    def _exact(self, q_raw, q_norm, wts):
+        acc, o = None, 0
+        for s, d in enumerate(self.dims):
+            qs = q_raw[:, o:o + d].double() / q_norm[s][:, None]
+            vs = self.raw[:, o:o + d].double() / self.norm[s][:, None]
+            e = wts[s] * (qs @ vs.T)
+            acc = e if acc is None else acc + e
+            o += d
+        return acc
+
+    def _exact_small(self, q_raw, q_norm, nq, k, wts, excl):
+        sc = self._exact(q_raw, q_norm, wts)
+        ids = torch.arange(self.n)
+        rows = [_sorted_topk(sc[r], ids, k, None if excl is None else int(excl[r]), self.index_offset) for r in range(nq)]
+        return torch.stack([r[0] for r in rows]), torch.stack([r[1] for r in rows])
+
+    def _sample(self, a_op, nq, step):
+        return (a_op[:nq].float() @ self.op[::step].T).float()
+
+    def _filter(self, a_op, nq, thr, cap, step=1):
+        sc = (a_op[:nq].float() @ self.op[::step].T).float()       # re-run passes hand over a bf16 operand
+        count = torch.zeros(nq, dtype=torch.int32)
+        c_s = torch.full((nq, cap), float("nan"), dtype=torch.float32)
+        c_i = torch.zeros((nq, cap), dtype=torch.int32)
+        for r in range(nq):
+            hit = torch.nonzero(sc[r] > thr[r]).flatten()
+            hit = hit[torch.randperm(len(hit), generator=torch.Generator().manual_seed(r))]   # arrival order is arbitrary
+            count[r] = len(hit)
+            m = min(len(hit), cap)
+            c_s[r, :m], c_i[r, :m] = sc[r, hit[:m]], hit[:m].int()
+        return count, c_s, c_i
+
+    def _sample_top(self, a_op, nq, step, big_j):
+        from cross_modal_video_engine_b200 import engine
+        n_s = (self.n + step - 1) // step
+        r = max(2, min(16, n_s // 2048))
+        coarse = self._sample(a_op, nq, step * r)
+        j0 = min(coarse.shape[1], int(math.ceil(4.0 * big_j / r)))
+        thr0 = engine._row_kth(coarse, None, j0, 0.0, 0)
+        cap_s = 1 << max(10, int(math.ceil(math.log2(16 * big_j))))
+        count, score, _ = self._filter(a_op, nq, thr0, cap_s, step=step)
+        return score, count, thr0
+
+    def _rescore_select(self, q_raw, q_norm, nq, k, wts, excl, cand, bound, thr, eps, certify):
+        count, c_s, c_i = cand
+        cap = c_s.shape[1]
+        exact_all = self._exact(q_raw[:nq], q_norm[:, :nq], wts)
+        out_s, out_i, cert, nxt = [], [], [], []
+        for r in range(nq):
+            n = min(int(count[r]), cap)
+            idx = c_i[r, :n].long()
+            sc = torch.where(c_s[r, :n] >= bound[r], exact_all[r, idx], torch.tensor(float("-inf"), dtype=torch.float64))
+            s, i, n_valid = _sorted_topk(sc, idx, k, None if excl is None else int(excl[r]), self.index_offset)
+            out_s.append(s)
+            out_i.append(i)
+            if certify:
+                c, x = _certify(float(s[k - 1]) if n_valid >= k else float("-inf"), n_valid, k, float(thr[r]), eps,
+                                int(count[r]) > cap, float(bound[r]))
+                cert.append(c)
+                nxt.append(x)
+        if certify:
+            return torch.stack(out_s), torch.stack(out_i), torch.tensor(cert, dtype=torch.int32), torch.tensor(nxt)
+        return torch.stack(out_s), torch.stack(out_i), None, None
+
+
+def patch_engine(monkeypatch_setattr):
+    """Swap engine._row_kth / _row_topj / _merge for torch-CPU statements of the same contracts."""
+    from cross_modal_video_engine_b200 import engine
+
+    def kth(row, j):
+        return float(torch.sort(row, descending=True).values[j - 1]) if 0 < j <= len(row) else float("-inf")
+
+    def row_kth(vals, counts, j1, sub, j2):
+        out = []
+        for r in range(vals.shape[0]):
+            n = vals.shape[1] if counts is None else min(int(counts[r]), vals.shape[1])
+            row = vals[r, :n]
+            v = kth(row, j1) - sub
+            if j2 > 0:
+                v = max(v, kth(row, j2))
+            out.append(v)
+        return torch.tensor(out, dtype=torch.float32)
+
+    def row_topj(vals, counts, j):
+        out = torch.full((vals.shape[0], j), float("-inf"), dtype=torch.float32)
+        for r in range(vals.shape[0]):
+            n = vals.shape[1] if counts is None else min(int(counts[r]), vals.shape[1])
+            top = torch.sort(vals[r, :n], descending=True).values[:j]
+            out[r, : len(top)] = top
+        return out
+
+    def merge(scores, idx, k, thr=None, eps=0.0, overflow=None):
+        rows = [_sorted_topk(scores[r], idx[r], k) for r in range(scores.shape[0])]
+        out_s, out_i = torch.stack([r[0] for r in rows]), torch.stack([r[1] for r in rows])
+        if thr is None:
+            return out_s, out_i
+        cert, nxt = [], []
+        for r, (s, _, n_valid) in enumerate(rows):
+            c, x = _certify(float(s[k - 1]) if n_valid >= k else float("-inf"), n_valid, k, float(thr[r]), eps,
+                            bool(overflow[r]) if overflow is not None else False, None)
+            cert.append(c)
+            nxt.append(x)
+        return out_s, out_i, torch.tensor(cert, dtype=torch.int32), torch.tensor(nxt)
+
+    monkeypatch_setattr(engine, "_row_kth", row_kth)
+    monkeypatch_setattr(engine, "_row_topj", row_topj)
+    monkeypatch_setattr(engine, "_merge", merge)

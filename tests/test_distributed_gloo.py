@@ -55,3 +55,52 @@ def test_two_rank_gather_and_merge(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
+
+
+def _pipeline_worker(rank, world, port, out_dir):
+    """search_shards over two gloo ranks with CPU model shards: global threshold, gathered bound, certified merge
+    and the re-run loop in lockstep (two queries overflow their candidate lists by construction)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cross_modal_video_engine_b200 import distributed, engine
+    import cpu_model
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cpu_model.patch_engine(setattr)
+    nv, nq, d, k = 40000, 12, 32, 20
+    g = torch.Generator().manual_seed(3)
+    V, Q = torch.randn((nv, d), generator=g), torch.randn((nq, d), generator=g)
+    grid = torch.randperm(nv, generator=g)[: 25 * nq].reshape(nq, 25)
+    for qi in range(nq):                                    # a few planted neighbours per query
+        V[grid[qi]] = Q[qi] + 0.3 * torch.randn((25, d), generator=g)
+    for qi in (1, 7):                                       # dense neighbourhoods: the candidate lists overflow
+        rows = torch.randperm(nv, generator=g)[:6000]
+        V[rows] = Q[qi] * 2.0 + 0.4 * torch.randn((6000, d), generator=g)
+    lo, hi = distributed.shard_range(nv, world, rank)
+    shard = cpu_model.ModelShard(V[lo:hi], (d,), index_offset=lo)
+    stats = {}
+    excl = torch.full((nq,), -1, dtype=torch.int64)
+    excl[::3] = grid[::3, 0]
+    s, i = engine.search_shards([shard], Q, k, exclude=excl, comm=distributed.GroupComm(), n_total=nv, small_nv=1000,
+                                stats=stats)
+    full = cpu_model.ModelShard(V, (d,))
+    _, qr, qn, _, _ = full.prepare_queries(Q, [1.0])
+    exact = full._exact(qr, qn, [1.0])
+    ref = [cpu_model._sorted_topk(exact[r], torch.arange(nv), k, int(excl[r])) for r in range(nq)]
+    ok = all(torch.equal(i[r], ref[r][1]) and torch.allclose(s[r], ref[r][0], rtol=0, atol=1e-12) for r in range(nq))
+    ok = ok and stats.get("reruns", 0) >= 1                  # the re-run loop did run, identically on both ranks
+    # small-corpus branch across ranks
+    s2, i2 = engine.search_shards([shard], Q, 5, comm=distributed.GroupComm(), n_total=nv, small_nv=10 ** 9)
+    ref2 = [cpu_model._sorted_topk(exact[r], torch.arange(nv), 5) for r in range(nq)]
+    ok = ok and all(torch.equal(i2[r], ref2[r][1]) for r in range(nq))
+    with open(os.path.join(out_dir, "prank%d" % rank), "w") as f:
+        f.write("ok" if ok else "mismatch")
+    dist.destroy_process_group()
+
+
+def test_two_rank_search_pipeline_on_cpu_model(tmp_path):
+    port = _free_port()
+    mp.spawn(_pipeline_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert open(os.path.join(str(tmp_path), "prank%d" % r)).read() == "ok"

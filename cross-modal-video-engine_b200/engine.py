@@ -422,36 +422,28 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
     live = [s for s in stores if s.n]
     # 2: one global threshold from the shards' samples
     big_j = max(pl["j"], pl["j_cap"])
-    if pl["n_sample"] >= 8192:
-        # two-level: the sample matrix (2.1 GB at 10 M rows) is never written or radix-selected
-        tops, floor = [], None
-        for s in live:
+    lists, floor = [], torch.full((nq,), float("-inf"), dtype=torch.float32, device=dev)
+    for s in live:
+        if (s.n + pl["step"] - 1) // pl["step"] >= 16384:
+            # two-level: the sample matrix (2.1 GB at 10 M rows) is never written or radix-selected
             sc, cnt, thr0 = s._sample_top(a_op, nq, pl["step"], big_j)
-            tops.append((sc, cnt))
-            floor = thr0 if floor is None else torch.minimum(floor, thr0)
-        if solo:
-            thr = _row_kth(tops[0][0], tops[0][1], pl["j"], 2.0 * eps, pl["j_cap"])
-        else:
-            lists = [_row_topj(sc, cnt, big_j) for sc, cnt in tops]
-            if not lists:
-                lists = [torch.full((nq, big_j), float("-inf"), dtype=torch.float32, device=dev)]
-                floor = torch.full((nq,), float("-inf"), dtype=torch.float32, device=dev)
-            thr = _row_kth(_union(lists, comm), None, pl["j"], 2.0 * eps, pl["j_cap"])
-            floor = -comm.max_(-floor)                                   # min over the ranks
-        # a list that came out too short gives -inf (or a value below the floor): fall back to the coarse floor,
-        # which ~0.4 % of the corpus exceeds -- far more than k rows, so it is below the k-th best score
-        thr = torch.maximum(thr, floor - 2.0 * eps)
-        del tops
+            lists.append((sc, cnt))
+            floor = thr0 if len(lists) == 1 else torch.minimum(floor, thr0)
+        else:                                                 # small shard: the few launches of the plain way win
+            lists.append((s._sample(a_op, nq, pl["step"]), None))
+            floor = torch.full_like(floor, float("-inf"))     # a complete list needs no floor
+    if solo:
+        thr = _row_kth(lists[0][0], lists[0][1], pl["j"], 2.0 * eps, pl["j_cap"])
     else:
-        samples = [s._sample(a_op, nq, pl["step"]) for s in live]
-        if solo:
-            thr = _row_kth(samples[0], None, pl["j"], 2.0 * eps, pl["j_cap"])
-        else:
-            lists = [_row_topj(sm, None, big_j) for sm in samples]
-            if not lists:
-                lists = [torch.full((nq, big_j), float("-inf"), dtype=torch.float32, device=dev)]
-            thr = _row_kth(_union(lists, comm), None, pl["j"], 2.0 * eps, pl["j_cap"])
-        del samples
+        tops = [_row_topj(sc, cnt, big_j) for sc, cnt in lists]
+        if not tops:
+            tops = [torch.full((nq, big_j), float("-inf"), dtype=torch.float32, device=dev)]
+        thr = _row_kth(_union(tops, comm), None, pl["j"], 2.0 * eps, pl["j_cap"])
+        floor = -comm.max_(-floor)                            # min over the ranks
+    # a two-level list that came out too short gives -inf (or a value below the floor): fall back to the coarse
+    # floor, which ~0.4 % of the corpus exceeds -- far more than k rows, so it is below the k-th best score
+    thr = torch.maximum(thr, floor - 2.0 * eps)
+    del lists
     ph.mark("sample_threshold")
     cap = pl["cap"] if solo else max(2048, min(pl["cap"], 1 << int(math.ceil(math.log2(4.0 * pl["cap"] / n_shards)))))
     n_shard_max = max(s.n for s in live) if live else 1

@@ -38,21 +38,20 @@ class BigFile:
         return self._mm
 
     def read(self, requested, isname=True):
-        """``(names, vectors)`` of the requested items in ascending row order; bigfile.py:22-52."""
-        requested = set(requested)
+        """``(names, vectors)`` of the requested items, de-duplicated and in ascending row order, vectors as Python
+        lists of the float32 values (what ``array('f').tolist()`` yields); unknown names are skipped, out-of-range
+        row numbers are an error -- the observable behaviour of bigfile.py:22-52."""
+        wanted = set(requested)
         if isname:
-            index_name_array = [(self.name2index[x], x) for x in requested if x in self.name2index]
+            picked = sorted(self.name2index[name] for name in wanted if name in self.name2index)
         else:
-            assert min(requested) >= 0
-            assert max(requested) < len(self.names)
-            index_name_array = [(x, self.names[x]) for x in requested]
-        if len(index_name_array) == 0:
+            picked = sorted(wanted)
+            if picked:
+                assert picked[0] >= 0 and picked[-1] < self.nr_of_images
+        if not picked:
             return [], []
-        index_name_array.sort(key=lambda v: v[0])
-        idx = np.fromiter((x[0] for x in index_name_array), dtype=np.int64, count=len(index_name_array))
-        vecs = np.asarray(self.rows()[idx], dtype=np.float32)
-        # array('f').tolist() in the reference yields Python floats of the float32 values
-        return [x[1] for x in index_name_array], [v.astype(np.float64).tolist() for v in vecs]
+        block = np.asarray(self.rows()[np.asarray(picked, dtype=np.int64)], dtype=np.float64)   # one gather, widened
+        return [self.names[r] for r in picked], block.tolist()
 
     def read_one(self, name):
         _, vectors = self.read([name])

@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: tools/sweep_sched.sh "ENV1=.. ENV2=.." ...   one line per configuration: sustained TFLOP/s of the filter
 # kernel (tools/score_bench.py, 2M-row corpus) and its DRAM traffic / L2 hit rate from a one-launch ncu read-out.
-CMD="python tools/score_bench.py --nv 2000000 --thr 0.0683 --cap 16384 --reps 3"
+CMD="python tools/score_bench.py --nv ${SWEEP_NV:-2000000} --nq ${SWEEP_NQ:-8192} --thr ${SWEEP_THR:-0.0683} --cap 16384 --reps 3"
 i=0
 for cfg in "$@"; do
   i=$((i+1))

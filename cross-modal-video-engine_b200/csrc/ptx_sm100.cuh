@@ -160,6 +160,42 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       : "r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
+// Cluster-scope variants for handing a value to the peer CTA through its shared memory: store + release-arrive on
+// the peer's barrier, acquire-wait on the local one.
+__device__ __forceinline__ void st_remote_u64(void* local_addr, uint32_t cta, uint64_t v) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.u64 [ra], %2;\n\t}"
+      :
+      : "r"(smem_u32(local_addr)), "r"(cta), "l"(v)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      :
+      : "r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 26)) {
+      printf("xmve: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
 // TMA load issued by either CTA of a pair; the bytes are accounted on the LEADER CTA's barrier
 // (bit 24 of the shared::cluster address selects the peer: clear it).
 __device__ __forceinline__ void tma_load_2d_pair(const void* desc, uint64_t* bar, void* smem_dst, int32_t c0,

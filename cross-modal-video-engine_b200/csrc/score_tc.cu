@@ -12,19 +12,20 @@
 //   FILTER  per-row window (lo, hi]: count scores above hi, append (score, index) of scores inside
 //           the window to a per-row candidate list -- the score matrix never reaches HBM.
 //
-// Tile shapes (XMVE_TILE = 0 | 1 | 2 overrides the choice made in launch()):
-//   SINGLE (0)  one CTA, tcgen05.mma.cta_group::1 of 128 x 256 x 16, two accumulator slots double-buffered (the
-//               epilogue of tile i overlaps the MMAs of tile i+1).  Chosen when the corpus streams from HBM: it
-//               reads every corpus line from DRAM once (95 % L2 hits) where the pair kernels re-fetch ~10x.
-//   PAIR (1)    two CTAs of a cluster drive one tcgen05.mma.cta_group::2 of 256 x 256 x 16: each CTA stages its
-//               128 query rows and HALF of the corpus tile (32 KB instead of 48 KB per SM and k-block).
-//   WIDE (2)    a CTA pair computes 256 queries x 512 corpus rows: per k-block each CTA stages its 128 query rows
+// Tile shapes (XMVE_TILE overrides the choice made in launch(): 0 / 1 / 2 with the static unit assignment,
+// 5 / 4 / 6 the same with the dynamic unit scheduler):
+//   SINGLE (0, 5)  one CTA, tcgen05.mma.cta_group::1 of 128 x 256 x 16, two accumulator slots double-buffered (the
+//               epilogue of tile i overlaps the MMAs of tile i+1).
+//   PAIR (1, 4)  two CTAs of a cluster drive one tcgen05.mma.cta_group::2 of 256 x 256 x 16: each CTA stages its
+//               128 query rows and HALF of the corpus tile (32 KB instead of 48 KB per SM and k-block).  Default
+//               (with the dynamic scheduler).
+//   WIDE (2, 6)  a CTA pair computes 256 queries x 512 corpus rows: per k-block each CTA stages its 128 query rows
 //               ONCE plus its halves of TWO corpus sub-tiles and the leader issues two cta_group::2 MMA chains that
 //               share the query operand (48 KB per SM per 1024 tensor clocks -- the fewest operand bytes per flop).
-//               Both accumulator slots belong to one tile, so the epilogue is not overlapped; 8 warps run it.
-//               Chosen when both operands are L2-resident (fastest there: +11 % over SINGLE, sustained).
-// The kernel runs at the 1 kW power cap (SM clock 1.1-1.4 GHz under load), so operand bytes moved per flop
-// decide the sustained rate, not tensor-pipe occupancy (profiles/r1_tile_schedule_sweep.md).
+//               Both accumulator slots belong to one tile, so the epilogue is not overlapped.
+// Unit assignment: static (worker, worker + n_workers, ...) or DYNAMIC -- a scheduler thread (warp 3 of the leader
+// CTA) takes the next unit from a global counter and hands it to the producer, MMA and epilogue roles of both CTAs
+// through a two-slot shared-memory mailbox, so the units of one corpus tile are always in flight together.
 //
 // Work is cut into units of ONE corpus tile x a group of query tiles, walked query-tile-major, inside
 // super-blocks of the query operand sized for L2 (see plan_schedule()).
@@ -37,6 +38,10 @@
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
+
+// Dynamic unit scheduler state (DYN kernels): the next unit to hand out; zeroed on the launch stream before every
+// DYN launch (launches of one process are serialised on one stream).
+__device__ unsigned long long xmve_sched_next = 0;
 
 namespace xmve {
 namespace {
@@ -222,7 +227,54 @@ __device__ __forceinline__ void epilogue_slot(const Params& p, uint32_t taddr, R
   }
 }
 
-template <int MODE, bool PAIR, int NB>
+// Unit sequence of one role (producer / MMA issuer / epilogue warp).  Static: worker, worker + n_workers, ...
+// Dynamic (DYN): the units are handed out one at a time by a scheduler thread through a two-slot mailbox in shared
+// memory, so that the units of one corpus tile are always taken within microseconds of each other -- with the
+// static assignment the workers sharing a corpus tile drift apart until each of them re-reads it from DRAM
+// (profiles/r1_tile_schedule_sweep.md section 7).
+template <bool DYN, bool PAIR>
+struct UnitFeed {
+  int64_t u, n_units;
+  int stride, slot;
+  uint32_t phase, rank;
+  uint64_t *full, *empty;
+  volatile int64_t* box;
+  __device__ __forceinline__ void init(int worker, int n_workers, int64_t n_units_, uint64_t* full_, uint64_t* empty_,
+                                       int64_t* box_, uint32_t rank_) {
+    u = static_cast<int64_t>(worker) - n_workers;
+    stride = n_workers;
+    n_units = n_units_;
+    slot = 0;
+    phase = 0;
+    full = full_;
+    empty = empty_;
+    box = box_;
+    rank = rank_;
+  }
+  // Every lane of the calling warp (WARP = true: all 32 lanes call it) or the single calling thread gets the next
+  // unit; false at the end.  `arrive`: this thread reports "read" for its role (lane 0 of a warp).
+  template <bool WARP>
+  __device__ __forceinline__ bool next(bool arrive) {
+    if (!DYN) {
+      u += stride;
+      return u < n_units;
+    }
+    if (PAIR && rank != 0) ptx::mbar_wait_cluster(&full[slot], phase);
+    else ptx::mbar_wait(&full[slot], phase);
+    u = box[slot];
+    if (WARP) __syncwarp();                                    // ALL lanes have read before lane 0 releases the slot
+    if (arrive) {                                              // the slot may be refilled once every role has read it
+      // cluster-scope release: the warp's reads of the mailbox must be performed before the leader may refill it
+      // (with the default CTA-scope arrive a peer warp busy storing results was seen to read the NEXT unit)
+      if (PAIR && rank != 0) ptx::mbar_arrive_remote_release(&empty[slot], 0);
+      else ptx::mbar_arrive(&empty[slot]);
+    }
+    if (++slot == 2) { slot = 0; phase ^= 1; }
+    return u < n_units;
+  }
+};
+
+template <int MODE, bool PAIR, int NB, bool DYN>
 __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const Params& p) {
   using C = Cfg<PAIR, NB>;
   extern __shared__ uint8_t smem_raw[];
@@ -231,7 +283,10 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tfull_bar = empty_bar + C::STAGES;
   uint64_t* tempty_bar = tfull_bar + ACC_SLOTS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + ACC_SLOTS);
+  uint64_t* sched_full = tempty_bar + ACC_SLOTS;                 // DYN: unit mailbox (2 slots)
+  uint64_t* sched_empty = sched_full + 2;
+  int64_t* sched_box = reinterpret_cast<int64_t*>(sched_empty + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_box + 2);
   uint2* park = reinterpret_cast<uint2*>(smem + C::STAGES * C::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;   // warp-uniform
@@ -252,6 +307,8 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
     for (int a = 0; a < ACC_SLOTS; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);                        // one tcgen05.commit
       ptx::mbar_init(&tempty_bar[a], (BN / C::EPI_COLS) * 4 * C::CTAS);   // one arrival per warp draining the slot
+      ptx::mbar_init(&sched_full[a], 1);                       // the scheduler thread
+      ptx::mbar_init(&sched_empty[a], 10 * C::CTAS - (PAIR ? 1 : 0));   // producer + 8 epilogue warps per CTA + MMA
     }
     ptx::fence_barrier_init();
   }
@@ -275,7 +332,10 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t u = worker; u < p.n_units; u += n_workers) {
+      UnitFeed<DYN, PAIR> feed;
+      feed.init(worker, n_workers, p.n_units, sched_full, sched_empty, sched_box, rank);
+      while (feed.template next<false>(true)) {
+        const int64_t u = feed.u;
         const Unit un = decode_unit(p, u, worker);
         const int b_row = un.t * C::TILE_N + static_cast<int>(rank) * C::B_ROWS;
         for (int i = 0; i < un.len; ++i) {
@@ -315,7 +375,10 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
       constexpr uint32_t idesc = ptx::idesc_bf16_f32(C::TILE_M, BN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int64_t u = worker; u < p.n_units; u += n_workers) {
+      UnitFeed<DYN, PAIR> feed;
+      feed.init(worker, n_workers, p.n_units, sched_full, sched_empty, sched_box, rank);
+      while (feed.template next<false>(true)) {
+        const int64_t u = feed.u;
         const Unit un = decode_unit(p, u, worker);
         for (int i = 0; i < un.len; ++i) {
           for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -355,6 +418,25 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
         }
       }
     }
+  } else if (warp == 3) {
+    // ================================ unit scheduler (DYN, leader CTA) ==============
+    if (DYN && lane == 0 && rank == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (;;) {
+        if (PAIR) ptx::mbar_wait_cluster(&sched_empty[slot], phase ^ 1);   // every role of the pair has read this slot
+        else ptx::mbar_wait(&sched_empty[slot], phase ^ 1);
+        const int64_t u = static_cast<int64_t>(atomicAdd(&xmve_sched_next, 1ull));
+        sched_box[slot] = u;
+        if (PAIR) {
+          ptx::st_remote_u64(&sched_box[slot], 1, static_cast<uint64_t>(u));
+          ptx::mbar_arrive_remote_release(&sched_full[slot], 1);
+        }
+        ptx::mbar_arrive(&sched_full[slot]);
+        if (u >= p.n_units) break;                             // the end marker has been handed out too
+        if (++slot == 2) { slot = 0; phase ^= 1; }
+      }
+    }
   } else if (warp >= EPI_WARP0) {
     // ================================ epilogue ====================================
     const int quarter = warp & 3;                              // TMEM lane quarter this warp may read
@@ -368,7 +450,10 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
     st.n = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t u = worker; u < p.n_units; u += n_workers) {
+    UnitFeed<DYN, PAIR> feed;
+    feed.init(worker, n_workers, p.n_units, sched_full, sched_empty, sched_box, rank);
+    while (feed.template next<true>(lane == 0)) {
+      const int64_t u = feed.u;
       const Unit un = decode_unit(p, u, worker);
       const int64_t col0 = static_cast<int64_t>(un.t) * C::TILE_N + sub * BN + col_in_slot;
       for (int i = 0; i < un.len; ++i) {
@@ -415,19 +500,38 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
 template <int MODE>
 __global__ void __launch_bounds__(Cfg<false, 1>::THREADS, 1)
 score_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
-  score_body<MODE, false, 1>(tm_a, tm_b, p);
+  score_body<MODE, false, 1, false>(tm_a, tm_b, p);
 }
 
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<true, 1>::THREADS, 1)
 score_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
-  score_body<MODE, true, 1>(tm_a, tm_b, p);
+  score_body<MODE, true, 1, false>(tm_a, tm_b, p);
 }
 
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<true, 2>::THREADS, 1)
 score_wide_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
-  score_body<MODE, true, 2>(tm_a, tm_b, p);
+  score_body<MODE, true, 2, false>(tm_a, tm_b, p);
+}
+
+// the same kernels with the dynamic unit scheduler
+template <int MODE>
+__global__ void __launch_bounds__(Cfg<false, 1>::THREADS, 1)
+score_dyn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
+  score_body<MODE, false, 1, true>(tm_a, tm_b, p);
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<true, 1>::THREADS, 1)
+score_pair_dyn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
+  score_body<MODE, true, 1, true>(tm_a, tm_b, p);
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<true, 2>::THREADS, 1)
+score_wide_dyn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
+  score_body<MODE, true, 2, true>(tm_a, tm_b, p);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -517,7 +621,7 @@ void plan_schedule(Params& p, int tile_m, int tile_n, int k, int workers) {
   if (const char* env = getenv("XMVE_HINT_B")) p.hint_b = hints[atoi(env) & 3];
 }
 
-template <int MODE, bool PAIR, int NB>
+template <int MODE, bool PAIR, int NB, bool DYN = false>
 int launch_cfg(const void* a_op, int64_t nq, int64_t a_ld, const void* b_op, int64_t nv, int64_t b_ld,
                int64_t b_row_step, int k, Params p, cudaStream_t stream) {
   using C = Cfg<PAIR, NB>;
@@ -536,30 +640,40 @@ int launch_cfg(const void* a_op, int64_t nq, int64_t a_ld, const void* b_op, int
   const int workers = static_cast<int>(p.n_units < workers_max ? p.n_units : workers_max);
   const int grid = workers * C::CTAS;
   void (*kern)(const CUtensorMap, const CUtensorMap, const Params) =
-      !PAIR ? score_kernel<MODE> : (NB == 2 ? score_wide_kernel<MODE> : score_pair_kernel<MODE>);
+      DYN ? (!PAIR ? score_dyn_kernel<MODE> : (NB == 2 ? score_wide_dyn_kernel<MODE> : score_pair_dyn_kernel<MODE>))
+          : (!PAIR ? score_kernel<MODE> : (NB == 2 ? score_wide_kernel<MODE> : score_pair_kernel<MODE>));
   static bool attr_set = false;                               // one flag per <MODE, PAIR, NB> instantiation
   if (!attr_set) {
     XMVE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
+  if (DYN) {
+    static void* next_addr = nullptr;
+    if (next_addr == nullptr) XMVE_CUDA(cudaGetSymbolAddress(&next_addr, xmve_sched_next));
+    XMVE_CUDA(cudaMemsetAsync(next_addr, 0, sizeof(unsigned long long), stream));
+  }
   kern<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tm_a, tm_b, p);
   return launch_status(!PAIR ? "score_kernel" : (NB == 2 ? "score_wide_kernel" : "score_pair_kernel"));
 }
 
-// Tile choice (measured, profiles/r1_tile_schedule_sweep.md).  When both operands fit in L2 the wide tile is the
-// fastest (it moves the fewest operand bytes per flop; the kernel runs at the 1 kW power cap, so bytes are
-// clocks).  When the corpus streams from HBM the CTA-pair kernels re-fetch corpus lines ~10x (72 % L2 hit rate,
-// 90-150 GB of DRAM reads for an 8.2 GB operand; cause not yet understood -- same schedule, same placement
-// under a cluster launch, L2 hints and k-rotation make no difference) while the single-CTA tile reads every
-// corpus line once (95 % hits) and sustains ~10 % more flop/s, so it is the choice for large corpora.
+// Tile choice (measured, profiles/r1_tile_schedule_sweep.md).  The kernel runs at the 1 kW power cap, so operand
+// bytes moved per flop decide the sustained rate.  The CTA-pair tile moves a third less than the single-CTA tile
+// and, with the DYNAMIC unit scheduler, reads every corpus line from DRAM once (16.4 GB for an 8.2 GB operand and
+// two query super-blocks; with the static assignment the workers sharing a corpus tile drifted apart and the pair
+// kernels re-read it ~10x): +5 % over the single-CTA tile at realistic candidate densities.  The wide tile moves
+// the fewest bytes but cannot overlap its epilogue; it wins only where nothing is appended (STORE) and both
+// operands are L2-resident.
 template <int MODE>
 int launch(const void* a_op, int64_t nq, int64_t a_ld, const void* b_op, int64_t nv, int64_t b_ld, int64_t b_row_step,
            int k, Params p, cudaStream_t stream) {
   const int64_t operand_bytes = (nq + nv) * static_cast<int64_t>(k) * 2;
-  int tile = operand_bytes <= (int64_t(48) << 20) ? (k >= 512 ? 2 : 1) : 0;
+  int tile = (MODE == MODE_STORE && operand_bytes <= (int64_t(48) << 20) && k >= 512) ? 2 : 4;
   if (const char* env = getenv("XMVE_TILE")) tile = atoi(env);
   if (tile == 2) return launch_cfg<MODE, true, 2>(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k, p, stream);
   if (tile == 1) return launch_cfg<MODE, true, 1>(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k, p, stream);
+  if (tile == 4) return launch_cfg<MODE, true, 1, true>(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k, p, stream);
+  if (tile == 5) return launch_cfg<MODE, false, 1, true>(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k, p, stream);
+  if (tile == 6) return launch_cfg<MODE, true, 2, true>(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k, p, stream);
   return launch_cfg<MODE, false, 1>(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k, p, stream);
 }
 

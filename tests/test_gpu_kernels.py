@@ -76,7 +76,7 @@ def test_prepare_rows(N, n, d, frames, dtype):
 SHAPES = [(1000, 1000, 1536), (77, 333, 100), (128, 256, 64), (129, 257, 192), (60, 70000, 2048), (513, 5000, 640)]
 
 
-@pytest.mark.parametrize("tile", [2, 1, 0])      # wide pair tile 256x512 / pair tile 256x256 / single-CTA 128x256
+@pytest.mark.parametrize("tile", [6, 5, 4, 2, 1, 0])   # 2 wide pair 256x512 / 1 pair 256x256 / 0 single-CTA 128x256; 6 / 4 / 5 = the same with the dynamic unit scheduler
 @pytest.mark.parametrize("nq,nv,d", SHAPES)
 def test_score_store_matches_fp32_matmul_of_the_operands(N, nq, nv, d, tile, monkeypatch):
     monkeypatch.setenv("XMVE_TILE", str(tile))
@@ -88,6 +88,27 @@ def test_score_store_matches_fp32_matmul_of_the_operands(N, nq, nv, d, tile, mon
     ref = -(a[:nq].double() @ b[:nv].double().T)
     err = (out.double() - ref).abs().max().item()
     assert err < 2e-6, "tcgen05 tile mismatch: max abs err %g" % err      # fp32 accumulation of exact products
+
+
+@pytest.mark.parametrize("tile", [6, 4, 1])
+def test_score_store_many_units_slow_epilogue(N, tile, monkeypatch):
+    """20 000 x 2 990 x 4608 (the fp32 cal_error of the MSR-VTT shape): thousands of work units, many of them empty,
+    and an epilogue that is busy storing -- the regime in which a mailbox hand-off with a too weak (CTA-scope)
+    release let a peer-CTA warp read the next unit.  Every output element must be written, and right."""
+    monkeypatch.setenv("XMVE_TILE", str(tile))
+    nq, nv, k = 20000, 2990, 4608
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.zeros((_rup(nq, 128), k), dtype=torch.bfloat16, device="cuda")
+    b = torch.zeros((_rup(nv, 256), k), dtype=torch.bfloat16, device="cuda")
+    a[:nq] = (torch.randn((nq, k), generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    b[:nv] = (torch.randn((nv, k), generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    for rep in range(3):
+        out = torch.full((nq, nv), float("nan"), dtype=torch.float32, device="cuda")
+        N.call("xmve_score_store", N.ptr(a), nq, a.stride(0), N.ptr(b), nv, b.stride(0), 1, k, -1.0, N.ptr(out), nv,
+               N.stream_ptr())
+        ref = -(a[:nq].float() @ b[:nv].float().T)
+        assert not torch.isnan(out).any(), "rep %d: %d elements never written" % (rep, int(torch.isnan(out).sum()))
+        assert float((out - ref).abs().max()) < 2e-4
 
 
 def test_score_store_x3_split_reaches_fp32_accuracy(N):
@@ -113,7 +134,7 @@ def test_score_store_strided_sample(N):
     assert (out.double() - ref).abs().max().item() < 2e-6
 
 
-@pytest.mark.parametrize("tile", [2, 1, 0])
+@pytest.mark.parametrize("tile", [6, 5, 4, 2, 1, 0])
 @pytest.mark.parametrize("nq,nv,d,use_hi", [(300, 50000, 512, False), (77, 3000, 100, True), (1000, 200000, 128, False)])
 def test_score_filter_window(N, nq, nv, d, use_hi, tile, monkeypatch):
     monkeypatch.setenv("XMVE_TILE", str(tile))

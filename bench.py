@@ -362,7 +362,7 @@ def run_b200_arm(args):
                     "note": "bytes are node totals: every rank uploads 1/N of the query batch (NVLink all-gather "
                             "completes it) and returns 1/N of the result rows"},
             "gpu_launches": launches,
-            "roofline": {"kernel": "score_kernel<FILTER> (tcgen05 score + threshold filter)", "bound": "tensor",
+            "roofline": {"kernel": "score_pair_dyn_kernel<FILTER> (tcgen05 cta_group::2 score + threshold filter, dynamic unit scheduler)", "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes": 2 * (hi - lo + nq) * sum(DIMS) + 8 * nq * k,

@@ -668,6 +668,7 @@ int launch(const void* a_op, int64_t nq, int64_t a_ld, const void* b_op, int64_t
            int k, Params p, cudaStream_t stream) {
   const int64_t operand_bytes = (nq + nv) * static_cast<int64_t>(k) * 2;
   int tile = (MODE == MODE_STORE && operand_bytes <= (int64_t(48) << 20) && k >= 512) ? 2 : 4;
+  if (nq <= BM) tile = 5;   // a handful of queries (AVS, online search): HBM-bound, half of a 256-row query tile is padding
   if (const char* env = getenv("XMVE_TILE")) tile = atoi(env);
   if (tile == 2) return launch_cfg<MODE, true, 2>(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k, p, stream);
   if (tile == 1) return launch_cfg<MODE, true, 1>(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k, p, stream);

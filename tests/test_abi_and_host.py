@@ -33,6 +33,18 @@ def test_binding_covers_the_header():
     assert set(_native.SIGNATURES) | {"xmve_last_error"} == set(_declared_symbols())
 
 
+def test_binding_argument_counts_match_the_header():
+    """Every ctypes signature has as many arguments as the prototype in include/xmve.h (ABI drift guard)."""
+    from cross_modal_video_engine_b200 import _native
+    with open(os.path.join(ROOT, "include", "xmve.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    protos = dict(re.findall(r"XMVE_API\s+(?:const\s+char\*|int)\s+(xmve_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S))
+    for name, args in _native.SIGNATURES.items():
+        params = protos[name].strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(args), "%s: header has %d parameters, the binding %d" % (name, n, len(args))
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_no_cpu_fallback():
     from cross_modal_video_engine_b200 import _native, engine, evaluation, metrics, validate

@@ -39,9 +39,11 @@
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
-// Dynamic unit scheduler state (DYN kernels): the next unit to hand out; zeroed on the launch stream before every
-// DYN launch (launches of one process are serialised on one stream).
-__device__ unsigned long long xmve_sched_next = 0;
+// Dynamic unit scheduler state (DYN kernels): the next unit to hand out.  Every launch takes the next counter of a
+// small ring and zeroes it on its own stream first, so launches that overlap on different streams do not share one
+// (up to 64 launches in flight).
+constexpr int SCHED_RING = 64;
+__device__ unsigned long long xmve_sched_next[SCHED_RING];
 
 namespace xmve {
 namespace {
@@ -82,6 +84,7 @@ struct Params {
   int m_tiles, n_tiles, m_group, n_mgroups, sb_tiles;   // m_tiles in units of TILE_M rows, n_tiles of TILE_N
   int64_t n_units, units_per_sb;
   uint64_t hint_a, hint_b;
+  unsigned long long* sched_next;   // DYN: this launch's unit counter
   // STORE
   float alpha;
   float* out;
@@ -426,7 +429,7 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
       for (;;) {
         if (PAIR) ptx::mbar_wait_cluster(&sched_empty[slot], phase ^ 1);   // every role of the pair has read this slot
         else ptx::mbar_wait(&sched_empty[slot], phase ^ 1);
-        const int64_t u = static_cast<int64_t>(atomicAdd(&xmve_sched_next, 1ull));
+        const int64_t u = static_cast<int64_t>(atomicAdd(p.sched_next, 1ull));
         sched_box[slot] = u;
         if (PAIR) {
           ptx::st_remote_u64(&sched_box[slot], 1, static_cast<uint64_t>(u));
@@ -621,6 +624,16 @@ void plan_schedule(Params& p, int tile_m, int tile_n, int k, int workers) {
   if (const char* env = getenv("XMVE_HINT_B")) p.hint_b = hints[atoi(env) & 3];
 }
 
+// The next counter of the ring, zeroed on `stream` (shared by every DYN kernel of the process).
+int take_sched_counter(unsigned long long** out, cudaStream_t stream) {
+  static void* ring = nullptr;
+  static unsigned launch_seq = 0;
+  if (ring == nullptr) XMVE_CUDA(cudaGetSymbolAddress(&ring, xmve_sched_next));
+  *out = static_cast<unsigned long long*>(ring) + (launch_seq++ % SCHED_RING);
+  XMVE_CUDA(cudaMemsetAsync(*out, 0, sizeof(unsigned long long), stream));
+  return XMVE_OK;
+}
+
 template <int MODE, bool PAIR, int NB, bool DYN = false>
 int launch_cfg(const void* a_op, int64_t nq, int64_t a_ld, const void* b_op, int64_t nv, int64_t b_ld,
                int64_t b_row_step, int k, Params p, cudaStream_t stream) {
@@ -648,9 +661,8 @@ int launch_cfg(const void* a_op, int64_t nq, int64_t a_ld, const void* b_op, int
     attr_set = true;
   }
   if (DYN) {
-    static void* next_addr = nullptr;
-    if (next_addr == nullptr) XMVE_CUDA(cudaGetSymbolAddress(&next_addr, xmve_sched_next));
-    XMVE_CUDA(cudaMemsetAsync(next_addr, 0, sizeof(unsigned long long), stream));
+    int s2 = take_sched_counter(&p.sched_next, stream);
+    if (s2 != XMVE_OK) return s2;
   }
   kern<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tm_a, tm_b, p);
   return launch_status(!PAIR ? "score_kernel" : (NB == 2 ? "score_wide_kernel" : "score_pair_kernel"));

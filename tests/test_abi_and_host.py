@@ -153,3 +153,31 @@ def test_encode_vid_and_text_keep_the_reference_layout():
     emb3, _ = evaluation.encode_text(lambda x: x.float(), Loader(False), "distill_from_best_model")
     assert emb3[:, 0].tolist() == [float(i) for i in range(7)]
     assert evaluation.encode_text(lambda x: x, Loader(False), "other") is None
+
+
+def test_search_pipeline_two_level_sampling_on_cpu_model(monkeypatch):
+    """The host pipeline on a CPU model of a shard (tests/cpu_model.py), at a size where the sampled threshold takes
+    the two-level path (coarse floor + filter over the strided sample): one shard, and the same corpus cut into
+    a large and a small shard (mixed sampling paths, global threshold) -- both must return the exact top-k."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cpu_model
+    from cross_modal_video_engine_b200 import engine
+    cpu_model.patch_engine(monkeypatch.setattr)
+    nv, nq, d, k = 2_200_000, 5, 16, 10
+    g = torch.Generator().manual_seed(7)
+    V, Q = torch.randn((nv, d), generator=g), torch.randn((nq, d), generator=g)
+    assert (nv + engine.plan(k, nv)["step"] - 1) // engine.plan(k, nv)["step"] >= 16384      # two-level regime
+    full = cpu_model.ModelShard(V, (d,))
+    _, qr, qn, _, _ = full.prepare_queries(Q, [1.0])
+    exact = full._exact(qr, qn, [1.0])
+    ref = [cpu_model._sorted_topk(exact[r], torch.arange(nv), k) for r in range(nq)]
+    stats = {}
+    s, i = engine.search_shards([full], Q, k, stats=stats)
+    assert all(torch.equal(i[r], ref[r][1]) for r in range(nq))
+    assert all(torch.allclose(s[r], ref[r][0], rtol=0, atol=1e-12) for r in range(nq))
+    assert 1e-3 < stats["eps"] < engine.EPS_X1
+    cut = 2_150_000                                                 # big shard: two-level; small shard: plain sample
+    shards = [cpu_model.ModelShard(V[:cut], (d,), 0), cpu_model.ModelShard(V[cut:], (d,), cut)]
+    s2, i2 = engine.search_shards(shards, Q, k)
+    assert all(torch.equal(i2[r], ref[r][1]) for r in range(nq))

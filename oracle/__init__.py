@@ -14,8 +14,11 @@ Pinning status
   from ``/root/reference/LINAS-engine``, runs it on seeded inputs and commits the results under
   ``tests/golden/``; ``tests/test_oracle_golden.py`` checks the restatement against them.
 * ``oracle.multifusion`` restates ``MultiFusion/src/validate.py:44-55,65-113,119,135-138`` and
-  ``MultiFusion/src/inference.py:51-66``.  Those modules need the pip packages ``clip``,
-  ``decord`` and ``h5py`` which are absent, so they cannot be imported: **parity unpinned** for
-  the MultiFusion restatement (only ``combiner.Combiner.time_process`` could be run; its golden is
-  committed too).
+  ``MultiFusion/src/inference.py:51-66``.  Those modules import pip packages that are absent here
+  (``clip``, ``decord``, ``h5py``, ``comet_ml``, ``ftfy``) but never touch them on the scoring path, so
+  ``oracle/make_golden_mf.py`` puts empty stand-ins into ``sys.modules``, imports the two reference modules
+  UNMODIFIED, replaces the one upstream call (``generate_cirr_val_predictions``: CLIP + Combiner) by seeded
+  predictions and runs ``validate.compute_cirr_val_metrics`` / ``inference.compute_cirr_val_metrics`` whole.
+  The 7-tuples, the ``results_wo_attn.npy`` top-100 name lists and the top-1 names are committed under
+  ``tests/golden/mf_cirr*``; ``tests/test_oracle_golden.py`` pins the restatement to them (bit-identical).
 """

@@ -1,8 +1,9 @@
 """torch-CPU fp32 restatement of MultiFusion's composed-retrieval scoring (oracle; test-only).
 
-PARITY UNPINNED: ``MultiFusion/src/validate.py`` and ``inference.py`` import the pip packages
-``clip``, ``decord`` and ``h5py`` which are not installed (no network), so the reference functions
-cannot be executed here.  What follows restates, line range by line range, the arithmetic of
+Pinned: ``oracle/make_golden_mf.py`` runs the UNMODIFIED ``MultiFusion/src/validate.py`` and ``inference.py``
+(stand-in modules for the absent ``clip`` / ``decord`` / ``h5py`` / ``comet_ml`` / ``ftfy`` imports, seeded
+predictions in place of the CLIP + Combiner call) and commits their outputs under ``tests/golden/mf_cirr*``;
+``tests/test_oracle_golden.py`` checks this file against them bit for bit.  It restates, line range by line range,
 
 * ``MultiFusion/src/validate.py:44-55``  index preparation (8-frame mean in 128-row chunks via
   ``Combiner.time_process`` = ``fea.mean(dim=1)``, combiner.py:140-143; then
@@ -13,8 +14,9 @@ cannot be executed here.  What follows restates, line range by line range, the a
 * ``MultiFusion/src/validate.py:135-141`` recall@1/5/10/50 (+ three constant -1 group recalls),
 * ``MultiFusion/src/inference.py:51,63-65`` the single-query top-1.
 
-Only ``Combiner.time_process`` could be imported and run; its output on a seeded input is
-committed under ``tests/golden/`` by ``oracle/make_golden.py``.
+``Combiner.time_process`` is additionally pinned on its own (``tests/golden/mf_time_process.npz``).  One
+deliberate difference: a query count that is a multiple of 32 makes the reference raise (empty trailing block,
+``reshape(0, -1)``, validate.py:96-97; recorded in the golden); the restatement evaluates the full blocks.
 """
 from __future__ import annotations
 

@@ -169,7 +169,7 @@ def test_c4_multifusion_shape(X):
                           plant=(torch.cat([target, reference]), torch.cat([tvec, rvec])))
     names = torch.randperm(10 * nv, device="cuda", generator=g)[:nv].cpu().numpy().astype(np.int64)
     t0 = time.time()
-    metrics, top_names = X.multifusion.compute_cirr_val_metrics(P, None, names, names[reference.cpu().numpy()],
+    metrics, top_names = X.multifusion.cirr_metrics_from_features(P, None, names, names[reference.cpu().numpy()],
                                                                 names[target.cpu().numpy()], store=store)
     torch.cuda.synchronize()
     t_all = time.time() - t0

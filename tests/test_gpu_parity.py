@@ -318,7 +318,7 @@ def test_search_edge_cases(X):
 def test_multifusion_metrics_and_ranked_names(X, n_index, n_query):
     index, q, names, ref, tgt = X.synth.composed_retrieval(5, n_index, n_query)
     (m_ref, top_ref) = mf_oracle.compute_cirr_val_metrics(torch.from_numpy(q), torch.from_numpy(index), names, ref, tgt)
-    (m_gpu, top_gpu) = X.multifusion.compute_cirr_val_metrics(torch.from_numpy(q), torch.from_numpy(index), names, ref, tgt)
+    (m_gpu, top_gpu) = X.multifusion.cirr_metrics_from_features(torch.from_numpy(q), torch.from_numpy(index), names, ref, tgt)
     assert m_gpu == m_ref
     assert m_ref[3] > 5.0                                       # the planted targets are actually retrieved
     # the oracle ranks in torch fp32, the engine in fp64: lists are identical except where two adjacent fp32

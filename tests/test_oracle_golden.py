@@ -77,3 +77,52 @@ def test_multifusion_time_process_golden(manifest):
         pytest.skip("reference combiner was not importable when goldens were minted")
     x = torch.from_numpy(synth.gaussian(31, 37 * 8, 640).reshape(37, 8, 640))
     np.testing.assert_array_equal(multifusion.time_process(x).numpy(), load_golden("mf_time_process")["pooled"])
+
+
+# ---- MultiFusion: the restatement against the UNMODIFIED reference functions (oracle/make_golden_mf.py) ----------
+def _mf_manifest():
+    with open(os.path.join(GOLDEN, "mf_cirr.json")) as f:
+        return json.load(f)
+
+
+def mf_case_inputs(rec, n_query=None):
+    from cross_modal_video_engine_b200 import synth
+    from conftest import input_sha256
+    out = synth.composed_retrieval(rec["seed"], rec["n_index"], n_query or rec["n_query"],
+                                   frames=rec.get("frames", 8), sigma=rec.get("sigma", 0.5))
+    return out
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c", "d"])
+def test_multifusion_oracle_matches_reference_validate(name):
+    """validate.compute_cirr_val_metrics (validate.py:27-143, unmodified) -> 7-tuple + results_wo_attn top-100."""
+    import torch
+    from conftest import input_sha256
+    from oracle import multifusion
+    rec = _mf_manifest()["cases"][name]
+    index, P, names, ref, tgt = mf_case_inputs(rec)
+    assert input_sha256(index, P, names, ref, tgt) == rec["input_sha256"], "synthetic generator drifted"
+    metrics, top = multifusion.compute_cirr_val_metrics(torch.from_numpy(P), torch.from_numpy(index), names, ref, tgt)
+    assert [float(x) for x in metrics] == rec["metrics"]                  # bit-identical floats
+    np.testing.assert_array_equal(top, load_golden("mf_cirr_" + name)["top100"])
+
+
+def test_multifusion_reference_cannot_take_a_multiple_of_32_queries():
+    """Recorded quirk: the empty trailing block of validate.py:71 raises in reshape(0, -1) (:96-97)."""
+    rec = _mf_manifest()["mult32"]
+    assert rec["n_query"] % 32 == 0 and rec.get("raises") == "RuntimeError"
+
+
+@pytest.mark.parametrize("name", ["i1", "i2"])
+def test_multifusion_oracle_matches_reference_inference(name):
+    """inference.compute_cirr_val_metrics (inference.py:26-66, unmodified) -> top-1 name."""
+    import torch
+    from conftest import input_sha256
+    from oracle import multifusion
+    rec = _mf_manifest()["inference"][name]
+    index, P, names, _, _ = mf_case_inputs(rec, n_query=3)
+    assert input_sha256(index, P, names) == rec["input_sha256"]
+    pooled = torch.from_numpy(index).mean(dim=1)
+    tar_list = ["vid_%d.mp4" % int(x) for x in names]
+    got = [multifusion.top1_name(torch.from_numpy(P[i:i + 1]), pooled, tar_list) for i in range(3)]
+    assert got == rec["top1"]

@@ -1,4 +1,5 @@
-"""Drop-in for ``LINAS-engine/validate.py``: ``norm_score`` (:7-11) and ``cal_perf`` (:15-54)."""
+"""Drop-in for ``LINAS-engine/validate.py``: ``norm_score`` (:7-11), ``cal_perf`` (:15-54) and the per-epoch
+``validate`` driver (:58-90, called from trainer.py:259,276)."""
 from __future__ import annotations
 
 import logging
@@ -7,7 +8,7 @@ import numpy as np
 import torch
 
 from . import _native as N
-from . import metrics
+from . import evaluation, metrics
 
 
 def norm_score(t2v_all_errors):
@@ -67,3 +68,49 @@ def cal_perf(t2v_all_errors, v2t_gt, t2v_gt, tb_logger=None, model=None):
             tb_logger.log_value(key, val, step=model.Eiters)
 
     return (v2t_r1, v2t_r5, v2t_r10, v2t_medr, v2t_meanr, v2t_map_score), (t2v_r1, t2v_r5, t2v_r10, t2v_medr, t2v_meanr, t2v_map_score)
+
+
+def validate(opt, tb_logger, vid_data_loader, text_data_loader, model, measure='cosine'):
+    """validate.py:58-90: encode the validation videos and captions, score, rank, and return the model-selection
+    score ``currscore`` (recall sum or mAP sum over the directions ``opt.direction`` names); logs ``rsum``.
+
+    Same control flow and the same ``opt`` fields (``style``, ``student_model``, ``val_metric``, ``direction``) as the
+    reference -- including its fall-through: a ``style`` other than 'distill_from_best_model' / 'GT' leaves
+    ``cap_embs`` unbound and raises ``UnboundLocalError``.  What differs is where the data lives: the embeddings stay
+    on the device (``evaluation.encode_*``), the errors matrix is produced and ranked there, and only the twelve
+    scalars come back.
+    """
+    # compute the encoding for all the validation video and captions
+    model.val_start()
+    if opt.style == 'distill_from_best_model' and opt.student_model == 'text+video':
+        video_embs, video_ids = evaluation.encode_vid(model.embed_vis_distill, vid_data_loader)
+    else:
+        video_embs, video_ids = evaluation.encode_vid(model.embed_vis, vid_data_loader)
+
+    if opt.style == 'distill_from_best_model':
+        cap_embs, caption_ids = evaluation.encode_text(model.embed_txt_distill, text_data_loader, opt.style)
+    elif opt.style == 'GT':
+        cap_embs, caption_ids = evaluation.encode_text(model.embed_txt_GT, text_data_loader, opt.style)
+
+    t2v_all_errors = evaluation.cal_error(video_embs, cap_embs, measure)
+    v2t_gt, t2v_gt = metrics.get_gt(video_ids, caption_ids)
+
+    (v2t_r1, v2t_r5, v2t_r10, v2t_medr, v2t_meanr, v2t_map_score), \
+        (t2v_r1, t2v_r5, t2v_r10, t2v_medr, t2v_meanr, t2v_map_score) = \
+        cal_perf(t2v_all_errors, v2t_gt, t2v_gt, tb_logger=tb_logger, model=model)
+
+    currscore = 0
+    if opt.val_metric == "recall":
+        if opt.direction == 'i2t' or opt.direction == 'all':
+            currscore += (v2t_r1 + v2t_r5 + v2t_r10)
+        if opt.direction == 't2i' or opt.direction == 'all':
+            currscore += (t2v_r1 + t2v_r5 + t2v_r10)
+    elif opt.val_metric == "map":
+        if opt.direction == 'i2t' or opt.direction == 'all':
+            currscore += v2t_map_score
+        if opt.direction == 't2i' or opt.direction == 'all':
+            currscore += t2v_map_score
+
+    tb_logger.log_value('rsum', currscore, step=model.Eiters)
+
+    return currscore

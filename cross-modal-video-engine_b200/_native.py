@@ -27,6 +27,8 @@ if not os.path.exists(LIB_PATH):
         "libxmve.so is not built (%s). Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
         "or `make -C cross-modal-video-engine_b200/csrc`. There is no CPU / PyTorch fallback." % LIB_PATH)
 
+import torch  # noqa: E402,F401  -- loads libcudart.so.12 into the process; libxmve.so links the runtime shared
+
 lib = C.CDLL(LIB_PATH)
 
 _p, _i, _l, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
@@ -49,7 +51,8 @@ SIGNATURES = {
     "xmve_score_f64": [_p, _l, _l, _p, _l, _l, _i, _d, _p, _l, _p],
     "xmve_pairwise_f64": [_p, _l, _l, _p, _l, _l, _i, _i, _d, _d, _p, _l, _p],
     "xmve_gt_ranks": [_p, _i, _l, _l, _l, _i, _p, _p, _l, _l, _i32, _p, _p],
-    "xmve_rank_metrics": [_p, _p, _l, _l, _i, _i, _p, _p, _p, _p, _p, _p],
+    "xmve_rank_metrics": [_p, _p, _l, _l, _i, _i, _i32, _p, _p, _p, _p, _p, _p, _p],
+    "xmve_list_ranks": [_p, _l, _l, _l, _p, _p, _l, _i32, _p, _p],
     "xmve_norm_score": [_p, _i, _l, _l, _l, _p, _l, _p, _p],
     "xmve_fuse_accumulate": [_p, _l, _p, _l, _i, _l, _l, _d, _i, _p],
 }
@@ -64,7 +67,7 @@ lib.xmve_last_error.restype = C.c_char_p
 launch_count = 0
 _LAUNCHES = {"xmve_prepare_rows": 1, "xmve_score_store": 1, "xmve_score_filter": 1, "xmve_row_kth": 1,
              "xmve_rescore": 1, "xmve_select_topk_i32": 1, "xmve_select_topk_i64": 1, "xmve_row_topj": 1, "xmve_normalize_f64": 1,
-             "xmve_score_f64": 1, "xmve_pairwise_f64": 1, "xmve_gt_ranks": 1, "xmve_rank_metrics": 1, "xmve_norm_score": 3, "xmve_fuse_accumulate": 1}
+             "xmve_score_f64": 1, "xmve_pairwise_f64": 1, "xmve_gt_ranks": 1, "xmve_rank_metrics": 1, "xmve_list_ranks": 1, "xmve_norm_score": 3, "xmve_fuse_accumulate": 1}
 
 
 def call(name, *args):

@@ -27,7 +27,7 @@ def _list_ranks(idx, relevant, n_mem):
     returns ``(off int64 [nq+1], rank int32 [n_entries], device)``."""
     idx = idx if torch.is_tensor(idx) else torch.as_tensor(np.asarray(idx))
     dev = idx.device if idx.is_cuda else torch.device("cuda", torch.cuda.current_device())
-    idx = idx.to(dev)
+    idx = idx.to(dev, torch.int64)
     nq, kk = idx.shape
     assert len(relevant) == nq, "one relevant set per query"
     sizes = np.fromiter((len(r) for r in relevant), dtype=np.int64, count=nq)
@@ -37,15 +37,10 @@ def _list_ranks(idx, relevant, n_mem):
     if int(off[-1]) == 0:
         return off_d, torch.zeros(1, dtype=torch.int32, device=dev), dev
     rel = torch.from_numpy(np.concatenate([np.asarray(r, dtype=np.int64).reshape(-1) for r in relevant])).to(dev)
-    owner = torch.repeat_interleave(torch.arange(nq, device=dev), torch.from_numpy(sizes).to(dev))
-    # sort the (query, row) keys of the lists once, look every relevant row up
-    big = int(n_mem) + 1
-    keys = (torch.arange(nq, device=dev).unsqueeze(1) * big + idx.clamp(min=-1) + 1).reshape(-1)   # -1 pad -> slot 0
-    skeys, order = torch.sort(keys)
-    want = owner * big + rel + 1
-    pos = torch.searchsorted(skeys, want).clamp(max=skeys.numel() - 1)
-    found = skeys[pos] == want
-    rank = torch.where(found, order[pos] % kk + 1, torch.full_like(pos, big)).to(torch.int32)
+    idx = idx.contiguous() if idx.stride(1) != 1 else idx
+    rank = torch.empty(int(off[-1]), dtype=torch.int32, device=dev)
+    N.call("xmve_list_ranks", N.ptr(idx), nq, kk, idx.stride(0), N.ptr(off_d), N.ptr(rel), int(off[-1]), int(n_mem) + 1,
+           N.ptr(rank), N.stream_ptr())
     return off_d, rank, dev
 
 
@@ -66,8 +61,8 @@ def ap_at_k(idx, relevant, n_shots, k=None):
     if nq == 0 or int(off_d[-1]) == 0:
         out = ap.cpu().numpy()
         return out, (np.mean(out) if nq else np.float64("nan"))
-    N.call("xmve_rank_metrics", N.ptr(rank), N.ptr(off_d), nq, int(n_shots), 0, int(k), None, N.ptr(ap), None, None,
-           None, N.stream_ptr())
+    from .metrics import rank_metrics
+    rank_metrics(rank, off_d, nq, n_shots, False, k, max(len(r) for r in relevant), None, ap, None, None)
     out = ap.cpu().numpy()
     return out, np.mean(out)
 

@@ -34,8 +34,8 @@ class APScorer:
         r = torch.from_numpy(ranks).to(dev)
         off = torch.tensor([0, ranks.size], dtype=torch.int64, device=dev)
         ap = torch.empty(1, dtype=torch.float64, device=dev)
-        N.call("xmve_rank_metrics", N.ptr(r), N.ptr(off), 1, len(labels), 0, int(self.k), None, N.ptr(ap), None, None,
-               None, N.stream_ptr())
+        from .metrics import rank_metrics
+        rank_metrics(r, off, 1, len(labels), False, self.k, int(ranks.size), None, ap, None, None)
         return float(ap.item())
 
 

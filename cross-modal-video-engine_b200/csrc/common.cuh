@@ -22,6 +22,18 @@ inline int fail(int code, const char* fmt, ...) {
 int require_sm100();      // XMVE_OK or XMVE_ERR_DEVICE (cached per device; api.cu)
 int sm_count();
 
+// Function attributes (opt-in shared memory) and __device__ symbol addresses belong to ONE device: every cache of
+// them is an array indexed by the current device ordinal, like the device gate in api.cu.
+constexpr int MAX_DEVICES = 64;
+inline int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) {
+    cudaGetLastError();
+    return -1;
+  }
+  return dev;
+}
+
 #define XMVE_CUDA(expr)                                                                    \
   do {                                                                                     \
     cudaError_t _e = (expr);                                                               \

@@ -47,14 +47,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must surface as a trapped kernel, never as a hung GPU.
+// Bounded wait: a pipeline bug must surface as a trapped kernel, never as a hung GPU.  The bound is WALL TIME
+// (%globaltimer, looked at every 2^16 polls), not a spin count: under compute-sanitizer, an ncu replay or a debugger
+// a legitimate wait can take orders of magnitude more polls.  -DXMVE_MBAR_TIMEOUT_S=0 disables the bound.
+#ifndef XMVE_MBAR_TIMEOUT_S
+#define XMVE_MBAR_TIMEOUT_S 20
+#endif
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __noinline__ void mbar_timeout_check(uint64_t& t0, const char* what) {
+  if (XMVE_MBAR_TIMEOUT_S == 0) return;
+  const uint64_t now = global_timer_ns();
+  if (t0 == 0) t0 = now;
+  else if (now - t0 > static_cast<uint64_t>(XMVE_MBAR_TIMEOUT_S) * 1000000000ull) {
+    printf("xmve: %s wait exceeded %d s (block %d thread %d)\n", what, XMVE_MBAR_TIMEOUT_S, blockIdx.x, threadIdx.x);
+    __trap();
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("xmve: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+    if ((++spins & 0xFFFFu) == 0) mbar_timeout_check(t0, "mbarrier");
   }
 }
 
@@ -182,6 +199,7 @@ __device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0, ok = 0;
+  uint64_t t0 = 0;
   while (!ok) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -190,10 +208,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
-    if (!ok && ++spins > (1u << 26)) {
-      printf("xmve: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+    if (!ok && (++spins & 0xFFFFu) == 0) mbar_timeout_check(t0, "cluster mbarrier");
   }
 }
 // TMA load issued by either CTA of a pair; the bytes are accounted on the LEADER CTA's barrier

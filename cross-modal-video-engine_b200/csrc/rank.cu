@@ -116,33 +116,48 @@ gt_ranks_cols_kernel(const T* __restrict__ x, int64_t n_row, int64_t n_col, int6
 }
 
 // One block per query: sort the query's ranks, reduce to best rank / AP, bump the global tallies.
+// The sort is a bitonic network whose compare-exchanges are ALL ascending (the first step of every merge mirrors its
+// block), so a list of any length n is sorted as if padded with +inf: exchanges with a partner >= n are skipped.
+// Lists of up to smem_cap entries are sorted in shared memory, longer ones in the caller's global scratch.
 __global__ void __launch_bounds__(128)
 rank_metrics_kernel(const int32_t* __restrict__ ranks, const int64_t* __restrict__ gt_off, int64_t n_mem,
-                    int first_only, int ap_k, int32_t* __restrict__ best, double* __restrict__ ap,
+                    int first_only, int ap_k, int smem_cap, int32_t* __restrict__ scratch,
+                    int32_t* __restrict__ best, double* __restrict__ ap,
                     unsigned long long* __restrict__ recall_counts, unsigned long long* __restrict__ rank_sum,
                     int32_t* __restrict__ hist) {
-  extern __shared__ int32_t s_rank[];
+  extern __shared__ int32_t s_rank_smem[];
   const int64_t q = blockIdx.x;
   const int64_t e0 = gt_off[q], e1 = gt_off[q + 1];
   const int n = static_cast<int>(e1 - e0);
+  int32_t* s_rank = n <= smem_cap ? s_rank_smem : scratch + e0;
   int P = 1;
   while (P < n) P <<= 1;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) s_rank[i] = i < n ? ranks[e0 + i] : 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s_rank[i] = ranks[e0 + i];
   __syncthreads();
   const int first_rank = n > 0 ? s_rank[0] : 0;               // rank of the FIRST ground-truth entry
   __syncthreads();
-  for (int size = 2; size <= P; size <<= 1)
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = threadIdx.x; t < P; t += blockDim.x) {
-        const int o = t ^ stride;
-        if (o > t) {
-          const bool asc = (t & size) == 0;
+  for (int size = 2; size <= P; size <<= 1) {
+    const int half = size >> 1;
+    for (int pr = threadIdx.x; pr < (P >> 1); pr += blockDim.x) {           // mirror step
+      const int blk = pr / half, j = pr - blk * half;
+      const int t = blk * size + j, o = blk * size + size - 1 - j;
+      if (o < n) {
+        const int a = s_rank[t], b = s_rank[o];
+        if (b < a) { s_rank[t] = b; s_rank[o] = a; }
+      }
+    }
+    __syncthreads();
+    for (int stride = half >> 1; stride > 0; stride >>= 1) {
+      for (int pr = threadIdx.x; pr < (P >> 1); pr += blockDim.x) {
+        const int t = 2 * stride * (pr / stride) + (pr % stride), o = t + stride;
+        if (o < n) {
           const int a = s_rank[t], b = s_rank[o];
-          if (asc ? (b < a) : (a < b)) { s_rank[t] = b; s_rank[o] = a; }
+          if (b < a) { s_rank[t] = b; s_rank[o] = a; }
         }
       }
       __syncthreads();
     }
+  }
   if (threadIdx.x == 0) {
     const int64_t length = (ap_k > 0 && ap_k <= n_mem) ? ap_k : n_mem;      // MetricScorer.getLength
     const int b = n > 0 ? s_rank[0] : static_cast<int>(n_mem + 1);
@@ -266,22 +281,79 @@ extern "C" int xmve_gt_ranks(const void* errors, int dtype, int64_t n_row, int64
   return launch_status("gt_ranks kernel");
 }
 
-extern "C" int xmve_rank_metrics(const int32_t* ranks, const int64_t* gt_off, int64_t n_query, int64_t n_mem,
-                                 int first_only, int ap_k, int32_t* best, double* ap, int64_t* recall_counts,
-                                 int64_t* rank_sum, int32_t* hist, void* stream) {
+namespace xmve {
+namespace {
+// One warp per CSR entry e: the 1-based position of wanted[e] in the ranked list of the query that owns e
+// (first occurrence), `absent` when it is not in the list.  The lanes scan the list with coalesced loads.
+__global__ void __launch_bounds__(256)
+list_ranks_kernel(const int64_t* __restrict__ lists, int64_t n_query, int64_t len, int64_t ld,
+                  const int64_t* __restrict__ off, const int64_t* __restrict__ wanted, int64_t n_entries, int32_t absent,
+                  int32_t* __restrict__ rank) {
+  const int64_t e = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (e >= n_entries) return;
+  int64_t lo = 0, hi = n_query;                                 // owner: the last q with off[q] <= e
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (off[mid] <= e) lo = mid; else hi = mid;
+  }
+  const int64_t* row = lists + lo * ld;
+  const int64_t w = wanted[e];
+  int32_t found = absent;
+  for (int64_t p0 = 0; p0 < len; p0 += 32) {
+    const int64_t p = p0 + lane;
+    const unsigned hit = __ballot_sync(0xffffffffu, p < len && row[p] == w);
+    if (hit != 0) {
+      found = static_cast<int32_t>(p0 + (__ffs(hit) - 1) + 1);
+      break;
+    }
+  }
+  if (lane == 0) rank[e] = found;
+}
+}  // namespace
+}  // namespace xmve
+
+extern "C" int xmve_list_ranks(const int64_t* lists, int64_t n_query, int64_t len, int64_t ld, const int64_t* off,
+                               const int64_t* wanted, int64_t n_entries, int32_t absent, int32_t* rank, void* stream) {
   using namespace xmve;
   XMVE_DEVICE_OR_RETURN();
-  XMVE_REQUIRE(ranks && gt_off && n_query >= 0 && n_mem > 0, "rank_metrics: bad arguments");
+  XMVE_REQUIRE(lists && off && rank && n_query > 0 && len > 0 && ld >= len && n_entries >= 0, "list_ranks: bad arguments");
+  if (n_entries == 0) return XMVE_OK;
+  XMVE_REQUIRE(wanted != nullptr, "list_ranks: wanted is null");
+  const int64_t blocks = (n_entries + 7) / 8;
+  if (blocks > 2147483647LL) return fail(XMVE_ERR_LIMIT, "list_ranks: too many entries");
+  list_ranks_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      lists, n_query, len, ld, off, wanted, n_entries, absent, rank);
+  return launch_status("list_ranks_kernel");
+}
+
+extern "C" int xmve_rank_metrics(const int32_t* ranks, const int64_t* gt_off, int64_t n_query, int64_t n_mem,
+                                 int first_only, int ap_k, int32_t max_gt, int32_t* sort_scratch, int32_t* best,
+                                 double* ap, int64_t* recall_counts, int64_t* rank_sum, int32_t* hist, void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  XMVE_REQUIRE(ranks && gt_off && n_query >= 0 && n_mem > 0 && max_gt >= 0, "rank_metrics: bad arguments");
   if (n_query == 0) return XMVE_OK;
-  const int smem = 16384 * static_cast<int>(sizeof(int32_t));      // up to 16384 GT entries per query
-  static bool attr_set = false;
-  if (!attr_set) {
-    XMVE_CUDA(cudaFuncSetAttribute(rank_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+  constexpr int SMEM_MAX = 16384;                                  // entries sorted in shared memory
+  if (max_gt > SMEM_MAX && sort_scratch == nullptr)
+    return fail(XMVE_ERR_LIMIT, "rank_metrics: a query has %d entries (> %d): pass sort_scratch (n_entries int32)",
+                max_gt, SMEM_MAX);
+  int cap = 32;
+  while (cap < max_gt && cap < SMEM_MAX) cap <<= 1;
+  const int smem = cap * static_cast<int>(sizeof(int32_t));
+  if (smem > 48 * 1024) {
+    static bool attr_set[MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (dev < 0) return fail(XMVE_ERR_DEVICE, "rank_metrics: no current device");
+    if (!attr_set[dev]) {
+      XMVE_CUDA(cudaFuncSetAttribute(rank_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     SMEM_MAX * static_cast<int>(sizeof(int32_t))));
+      attr_set[dev] = true;
+    }
   }
   rank_metrics_kernel<<<static_cast<unsigned>(n_query), 128, smem, static_cast<cudaStream_t>(stream)>>>(
-      ranks, gt_off, n_mem, first_only, ap_k, best, ap, reinterpret_cast<unsigned long long*>(recall_counts),
-      reinterpret_cast<unsigned long long*>(rank_sum), hist);
+      ranks, gt_off, n_mem, first_only, ap_k, cap, sort_scratch, best, ap,
+      reinterpret_cast<unsigned long long*>(recall_counts), reinterpret_cast<unsigned long long*>(rank_sum), hist);
   return launch_status("rank_metrics_kernel");
 }
 

@@ -36,6 +36,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -625,12 +627,15 @@ void plan_schedule(Params& p, int tile_m, int tile_n, int k, int workers) {
   if (const char* env = getenv("XMVE_HINT_B")) p.hint_b = hints[atoi(env) & 3];
 }
 
-// The next counter of the ring, zeroed on `stream` (shared by every DYN kernel of the process).
+// The next counter of the current device's ring, zeroed on `stream` (shared by every DYN kernel of the process;
+// a __device__ symbol has one address per device).
 int take_sched_counter(unsigned long long** out, cudaStream_t stream) {
-  static void* ring = nullptr;
-  static unsigned launch_seq = 0;
-  if (ring == nullptr) XMVE_CUDA(cudaGetSymbolAddress(&ring, xmve_sched_next));
-  *out = static_cast<unsigned long long*>(ring) + (launch_seq++ % SCHED_RING);
+  static void* ring[MAX_DEVICES] = {};
+  static std::atomic<unsigned> launch_seq{0};
+  const int dev = current_device();
+  if (dev < 0) return fail(XMVE_ERR_DEVICE, "score: no current device");
+  if (ring[dev] == nullptr) XMVE_CUDA(cudaGetSymbolAddress(&ring[dev], xmve_sched_next));
+  *out = static_cast<unsigned long long*>(ring[dev]) + (launch_seq.fetch_add(1) % SCHED_RING);
   XMVE_CUDA(cudaMemsetAsync(*out, 0, sizeof(unsigned long long), stream));
   return XMVE_OK;
 }
@@ -656,10 +661,12 @@ int launch_cfg(const void* a_op, int64_t nq, int64_t a_ld, const void* b_op, int
   void (*kern)(const CUtensorMap, const CUtensorMap, const Params) =
       DYN ? (!PAIR ? score_dyn_kernel<MODE> : (NB == 2 ? score_wide_dyn_kernel<MODE> : score_pair_dyn_kernel<MODE>))
           : (!PAIR ? score_kernel<MODE> : (NB == 2 ? score_wide_kernel<MODE> : score_pair_kernel<MODE>));
-  static bool attr_set = false;                               // one flag per <MODE, PAIR, NB> instantiation
-  if (!attr_set) {
+  static bool attr_set[MAX_DEVICES] = {};                     // per <MODE, PAIR, NB, DYN> instantiation and device
+  const int dev = current_device();
+  if (dev < 0) return fail(XMVE_ERR_DEVICE, "score: no current device");
+  if (!attr_set[dev]) {
     XMVE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   if (DYN) {
     int s2 = take_sched_counter(&p.sched_next, stream);

@@ -263,11 +263,12 @@ int launch_select(const double* score, const IdxT* idx, int64_t rows, int64_t co
     if (pmax < k) return fail(XMVE_ERR_LIMIT, "select_topk: k too large");
   }
   const int smem_bytes = pmax * static_cast<int>(sizeof(double) + sizeof(IdxT));
-  static int attr_bytes[2] = {0, 0};
-  const int which = sizeof(IdxT) == 4 ? 0 : 1;
-  if (smem_bytes > attr_bytes[which]) {
+  static int attr_bytes[MAX_DEVICES] = {};                 // per <IdxT> instantiation and per device
+  const int dev = current_device();
+  if (dev < 0) return fail(XMVE_ERR_DEVICE, "select_topk: no current device");
+  if (smem_bytes > attr_bytes[dev]) {
     XMVE_CUDA(cudaFuncSetAttribute(select_topk_kernel<IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_bytes[which] = smem_bytes;
+    attr_bytes[dev] = smem_bytes;
   }
   select_topk_kernel<IdxT><<<static_cast<unsigned>(rows), 512, smem_bytes, st>>>(
       score, idx, cols, counts, idx_offset, exclude, k, thr, eps, bound, overflow, pmax, out_score, out_idx, out_valid,

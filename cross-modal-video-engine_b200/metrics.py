@@ -52,6 +52,20 @@ def _csr(gts, n_query):
     return off, ids, int(counts.max()) if n_query else 0
 
 
+#: lists longer than this are sorted in a global scratch buffer instead of shared memory (xmve_rank_metrics)
+SORT_SMEM_ENTRIES = 16384
+
+
+def rank_metrics(ranks, off, n_query, n_mem, first_only, ap_k, max_gt, best=None, ap=None, tallies=None, hist=None):
+    """``xmve_rank_metrics`` with the scratch a query of more than 16384 ground-truth entries needs."""
+    scratch = None
+    if max_gt > SORT_SMEM_ENTRIES:
+        scratch = torch.empty(ranks.numel(), dtype=torch.int32, device=ranks.device)
+    N.call("xmve_rank_metrics", N.ptr(ranks), N.ptr(off), int(n_query), int(n_mem), 1 if first_only else 0, int(ap_k),
+           int(max_gt), N.ptr(scratch), N.ptr(best), N.ptr(ap), N.ptr(tallies),
+           N.ptr(tallies[3:]) if tallies is not None else None, N.ptr(hist), N.stream_ptr())
+
+
 def _device_matrix(scores):
     N.require_device()
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -87,6 +101,7 @@ class RankResult:
         N.call("xmve_gt_ranks", N.ptr(x), N.F64 if x.dtype == torch.float64 else N.F32, n_row, n_col, x.stride(0),
                axis, N.ptr(self.off), N.ptr(self.ids), self.n_query, n_entries, max_gt, N.ptr(self.ranks), st)
         self._x = x
+        self.max_gt = max_gt
         self.reduce(first_only, ap_k)
 
     def reduce(self, first_only=False, ap_k=0):
@@ -95,9 +110,8 @@ class RankResult:
         self.ap = torch.empty(self.n_query, dtype=torch.float64, device=dev)
         self.tallies = torch.zeros(4, dtype=torch.int64, device=dev)          # r<=1, r<=5, r<=10, sum of ranks
         self.hist = torch.zeros(self.n_mem + 2, dtype=torch.int32, device=dev)
-        N.call("xmve_rank_metrics", N.ptr(self.ranks), N.ptr(self.off), self.n_query, self.n_mem,
-               1 if first_only else 0, int(ap_k), N.ptr(self.best), N.ptr(self.ap), N.ptr(self.tallies),
-               N.ptr(self.tallies[3:]), N.ptr(self.hist), st)
+        rank_metrics(self.ranks, self.off, self.n_query, self.n_mem, first_only, ap_k, self.max_gt, self.best, self.ap,
+                     self.tallies, self.hist)
         return self
 
     def recall_medr_meanr(self):
@@ -152,12 +166,12 @@ def eval_q2m_topk(idx, q2m_gts, n_m):
     from .avs import _list_ranks
     N_.require_device()
     n_q, k = idx.shape
-    off, rank, dev = _list_ranks(idx, [q2m_gts[i] for i in range(n_q)], n_m)
+    gts = [q2m_gts[i] for i in range(n_q)]
+    off, rank, dev = _list_ranks(idx, gts, n_m)
     best = torch.empty(n_q, dtype=torch.int32, device=dev)
     tallies = torch.zeros(4, dtype=torch.int64, device=dev)
     hist = torch.zeros(n_m + 2, dtype=torch.int32, device=dev)
-    N_.call("xmve_rank_metrics", N_.ptr(rank), N_.ptr(off), n_q, int(n_m), 0, 0, N_.ptr(best), None, N_.ptr(tallies),
-            N_.ptr(tallies[3:]), N_.ptr(hist), N_.stream_ptr())
+    rank_metrics(rank, off, n_q, n_m, False, 0, max((len(g) for g in gts), default=0), best, None, tallies, hist)
     c1, c5, c10, rsum = (int(v) for v in tallies.cpu().tolist())
     n_found = int((best <= k).sum())
     r1, r5, r10 = 100.0 * c1 / n_q, 100.0 * c5 / n_q, 100.0 * c10 / n_q

@@ -201,11 +201,22 @@ XMVE_API int xmve_gt_ranks(const void* errors, int dtype, int64_t n_row, int64_t
  *               ascending, ap += j / rank_j in that order, / nr_relevant (basic/metric.py:31-46);
  *               first_only != 0 marks only the FIRST GT entry (t2v_map, util/metrics.py:72-73)
  *   recall_counts[0..2] += #{best <= 1, 5, 10}; rank_sum += best; hist[best] += 1 (hist[n_mem+2])
+ * max_gt = the largest number of entries of any query (the caller built the CSR).  Lists of up to 16384 entries are
+ * sorted in shared memory; beyond that sort_scratch (int32 [n_entries], DEVICE) is required (XMVE_ERR_LIMIT without it)
+ * and the longer lists are sorted there.
  */
 XMVE_API int xmve_rank_metrics(const int32_t* ranks, const int64_t* gt_off, int64_t n_query, int64_t n_mem,
-                      int first_only, int ap_k,
+                      int first_only, int ap_k, int32_t max_gt, int32_t* sort_scratch,
                       int32_t* best, double* ap, int64_t* recall_counts, int64_t* rank_sum,
                       int32_t* hist, void* stream);
+
+/* Ranks from top-k LISTS instead of a score matrix (corpora whose matrix cannot exist): lists int64 [n_query, len]
+ * (row stride ld) are ranked memory ids (np.argsort(errors)[:topK], LINAS-engine/inference.py:79-80); for CSR entry e
+ * of query q (off[n_query+1], wanted[n_entries]) rank[e] = 1 + the position of wanted[e] in row q, or `absent` when
+ * the list does not hold it.  Feeds xmve_rank_metrics (AP@k of basic/metric.py:31-46, R@K of util/metrics.py:149-151).
+ */
+XMVE_API int xmve_list_ranks(const int64_t* lists, int64_t n_query, int64_t len, int64_t ld, const int64_t* off,
+                    const int64_t* wanted, int64_t n_entries, int32_t absent, int32_t* rank, void* stream);
 
 /* ---- norm_score (LINAS-engine/validate.py:7-11) -------------------------------------------------
  * minmax[0] = min(-E), minmax[1] = max(-E - min) over the whole matrix (two launches inside);

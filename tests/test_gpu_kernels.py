@@ -330,3 +330,87 @@ def test_score_f64_and_normalize(N):
     out = torch.empty((nq, nv), dtype=torch.float64, device="cuda")
     N.call("xmve_score_f64", N.ptr(qn), nq, d, N.ptr(vn), nv, d, d, -1.0, N.ptr(out), nv, N.stream_ptr())
     torch.testing.assert_close(out, -(qn @ vn.T), rtol=0, atol=1e-14)
+
+
+# ---- rank / metric kernels ------------------------------------------------------------------------------
+def _ap_reference(ranks, n_mem, k, first_only=False):
+    """APScorer(k).score (basic/metric.py:25-46) from the 1-based ranks of the relevant entries."""
+    length = k if 0 < k <= n_mem else n_mem
+    if len(ranks) == 0:
+        return 0.0
+    if first_only:
+        return 1.0 / ranks[0] if ranks[0] <= length else 0.0
+    ap, hit = 0.0, 0
+    for r in sorted(ranks):
+        if r > length:
+            break
+        hit += 1
+        ap += hit / r
+    return ap / len(ranks)
+
+
+@pytest.mark.parametrize("sizes", [[0, 1, 5, 33, 1000], [16384, 3], [16385, 7, 40000, 0, 2]])
+def test_rank_metrics_any_list_length(N, sizes):
+    """Per-query sort + reductions; lists of more than 16384 entries (they overran the shared buffer)
+    are sorted in the global scratch.  Without the scratch the call must fail with XMVE_ERR_LIMIT."""
+    from cross_modal_video_engine_b200 import metrics
+    rng = np.random.default_rng(5)
+    n_mem = 100000
+    lists = [rng.permutation(n_mem)[:s] + 1 for s in sizes]
+    off = np.zeros(len(sizes) + 1, np.int64)
+    np.cumsum(sizes, out=off[1:])
+    ranks = torch.from_numpy(np.concatenate(lists).astype(np.int32)).cuda()
+    off_d = torch.from_numpy(off).cuda()
+    for first_only, k in ((False, 0), (False, 1000), (True, 0)):
+        best = torch.empty(len(sizes), dtype=torch.int32, device="cuda")
+        ap = torch.empty(len(sizes), dtype=torch.float64, device="cuda")
+        tallies = torch.zeros(4, dtype=torch.int64, device="cuda")
+        hist = torch.zeros(n_mem + 2, dtype=torch.int32, device="cuda")
+        metrics.rank_metrics(ranks, off_d, len(sizes), n_mem, first_only, k, max(sizes), best, ap, tallies, hist)
+        want_best = [int(min(l)) if len(l) else n_mem + 1 for l in lists]
+        assert best.cpu().tolist() == want_best
+        assert ap.cpu().tolist() == [_ap_reference([int(x) for x in l], n_mem, k, first_only) for l in lists]
+        assert tallies.cpu().tolist() == [sum(b <= t for b in want_best) for t in (1, 5, 10)] + [sum(want_best)]
+        assert int(hist.sum()) == len(sizes)
+    if max(sizes) > 16384:
+        with pytest.raises(N.XmveError, match="sort_scratch"):
+            N.call("xmve_rank_metrics", N.ptr(ranks), N.ptr(off_d), len(sizes), n_mem, 0, 0, max(sizes), None, None,
+                   N.ptr(ap), None, None, None, N.stream_ptr())
+
+
+def test_list_ranks(N):
+    rng = np.random.default_rng(6)
+    nq, kk, n_mem = 37, 1000, 50000
+    lists = np.stack([rng.permutation(n_mem)[:kk] for _ in range(nq)]).astype(np.int64)
+    lists[3, 500:] = -1                                                  # a padded list
+    sizes = rng.integers(0, 40, nq)
+    wanted = [np.concatenate([rng.choice(lists[q, :400], sizes[q] // 2, replace=False),
+                              rng.integers(0, n_mem, sizes[q] - sizes[q] // 2)]) for q in range(nq)]
+    off = np.zeros(nq + 1, np.int64)
+    np.cumsum(sizes, out=off[1:])
+    flat = np.concatenate(wanted).astype(np.int64)
+    rank = torch.empty(len(flat), dtype=torch.int32, device="cuda")
+    l_d = torch.from_numpy(lists).cuda()
+    N.call("xmve_list_ranks", N.ptr(l_d), nq, kk, kk, N.ptr(torch.from_numpy(off).cuda()),
+           N.ptr(torch.from_numpy(flat).cuda()), len(flat), n_mem + 1, N.ptr(rank), N.stream_ptr())
+    want = []
+    for q in range(nq):
+        pos = {int(v): p + 1 for p, v in reversed(list(enumerate(lists[q]))) if v >= 0}
+        want += [pos.get(int(w), n_mem + 1) for w in wanted[q]]
+    assert rank.cpu().tolist() == want
+
+
+def test_ap_at_k_with_a_huge_relevant_set(N):
+    """avs.ap_at_k with 20 000 relevant shots for one query (> the 16384-entry shared sort)."""
+    from cross_modal_video_engine_b200 import avs
+    rng = np.random.default_rng(7)
+    n_shots, kk = 200000, 1000
+    idx = np.stack([rng.permutation(n_shots)[:kk] for _ in range(2)]).astype(np.int64)
+    relevant = [np.concatenate([idx[0, ::3], rng.integers(0, n_shots, 20000)]), idx[1, :5]]
+    relevant[0] = np.unique(relevant[0])
+    ap, m = avs.ap_at_k(torch.from_numpy(idx).cuda(), relevant, n_shots, 1000)
+    for q in range(2):
+        pos = {int(v): p + 1 for p, v in enumerate(idx[q])}
+        ranks = [pos.get(int(r), n_shots + 1) for r in relevant[q]]
+        assert ap[q] == _ap_reference(ranks, n_shots, 1000)
+    assert m == np.mean(ap)

@@ -372,8 +372,19 @@ def run_b200_arm(args):
 
     engine.N.call = timed_call
 
+    # The certificate of a step (one int32: how many rows need a re-run) comes back asynchronously; it is resolved
+    # one step late, so the host enqueues step i+1 while the GPU still scores step i.  The last step of a timed
+    # region is resolved INSIDE the region (finish_device).
+    in_flight = []
+
     def step_device():
-        return distributed.sharded_search(store, q_dev, k, weights=WEIGHTS, n_total=args.nv)
+        in_flight.append(distributed.sharded_search(store, q_dev, k, weights=WEIGHTS, n_total=args.nv, defer=True))
+        if len(in_flight) > 1:
+            in_flight.pop(0).result()
+
+    def finish_device():
+        while in_flight:
+            in_flight.pop(0).result()
 
     r_lo, r_hi = distributed.shard_range(nq, world, rank)   # result rows this rank hands back to the host
 
@@ -381,10 +392,15 @@ def run_b200_arm(args):
         # host buffers in, host buffers out: the batch crosses PCIe once per node (each rank uploads its slice,
         # NVLink all-gather), every rank returns its slice of the result rows
         q = distributed.upload_rows(q_host, device=device)
-        s, i = distributed.sharded_search(store, q, k, weights=WEIGHTS, n_total=args.nv)
-        out_s_host[r_lo:r_hi].copy_(s[r_lo:r_hi], non_blocking=True)
-        out_i_host[r_lo:r_hi].copy_(i[r_lo:r_hi], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        p = distributed.sharded_search(store, q, k, weights=WEIGHTS, n_total=args.nv, defer=True)
+        out_s_host[r_lo:r_hi].copy_(p.scores[r_lo:r_hi], non_blocking=True)
+        out_i_host[r_lo:r_hi].copy_(p.idx[r_lo:r_hi], non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # ONE host sync per step: results + certificate count
+        s, i = p.result()
+        if p.reran:                                         # rows were re-run: hand the corrected lists back
+            out_s_host[r_lo:r_hi].copy_(s[r_lo:r_hi], non_blocking=True)
+            out_i_host[r_lo:r_hi].copy_(i[r_lo:r_hi], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
         return s, i
 
     def barrier():
@@ -392,12 +408,14 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()
         t1.record()
         barrier()
         ms = t0.elapsed_time(t1)
@@ -409,10 +427,11 @@ def run_b200_arm(args):
 
     for _ in range(max(args.warmup, 3)):
         step_device()
+    finish_device()
     sampler = ClockSampler(local) if rank == 0 else None
     filt_events.clear()
     launches0 = _native.launch_count
-    ms_total = timed(step_device, args.steps)
+    ms_total = timed(step_device, args.steps, finish_device)
     launches = _native.launch_count - launches0
     filt_ms = [a.elapsed_time(b) for a, b in filt_events]
     clocks = sampler.stop() if sampler else None

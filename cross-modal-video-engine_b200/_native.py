@@ -42,10 +42,14 @@ SIGNATURES = {
     "xmve_prepare_rows": [_p, _i, _l, _i, _i, _l, _p, _l, _l, _p, _p, _p, _l, _l, _i, _f, _i, _p],
     "xmve_score_store": [_p, _l, _l, _p, _l, _l, _l, _i, _f, _p, _l, _p],
     "xmve_score_filter": [_p, _l, _l, _p, _l, _l, _l, _i, _p, _p, _p, _p, _p, _p, _i32, _p],
-    "xmve_row_kth": [_p, _l, _l, _l, _p, _i32, _f, _i32, _p, _p],
-    "xmve_rescore": [_p, _l, _l, _p, _p, _l, _l, _p, _i, _p, _p, _i, _p, _p, _p, _i32, _p, _p, _p],
-    "xmve_select_topk_i32": [_p, _p, _l, _l, _p, _l, _p, _i32, _p, _f, _p, _p, _p, _p, _p, _p, _p],
-    "xmve_select_topk_i64": [_p, _p, _l, _l, _p, _i32, _p, _f, _p, _p, _p, _p, _p, _p, _p],
+    "xmve_row_kth": [_p, _l, _l, _l, _p, _i32, _f, _p, _i32, _p, _p],
+    "xmve_rescore": [_p, _l, _l, _p, _p, _l, _l, _p, _i, _p, _p, _i, _p, _p, _p, _i32, _p, _p, _p, _p],
+    "xmve_pilot_top": [_p, _p, _p, _l, _i32, _l, _p, _i32, _p, _p],
+    "xmve_pilot_bound": [_p, _i32, _l, _i32, _i32, _f, _p, _p, _p],
+    "xmve_eps_bound": [_p, _i32, _l, _p, _d, _i32, _f, _p, _p],
+    "xmve_select_topk_i32": [_p, _p, _l, _l, _p, _l, _p, _i32, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "xmve_select_topk_i64": [_p, _p, _l, _l, _p, _i32, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "xmve_merge_topk_packed": [_p, _i32, _l, _l, _i32, _p, _i32, _p, _f, _p, _p, _p, _p, _p, _p, _p],
     "xmve_row_topj": [_p, _l, _l, _l, _p, _i32, _p, _p],
     "xmve_normalize_f64": [_p, _i, _l, _i, _l, _p, _l, _i, _p],
     "xmve_score_f64": [_p, _l, _l, _p, _l, _l, _i, _d, _p, _l, _p],
@@ -60,13 +64,15 @@ for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name)
     _fn.argtypes = _args
     _fn.restype = _i
+lib.xmve_packed_topk_bytes.argtypes = [_l, _i32]
+lib.xmve_packed_topk_bytes.restype = C.c_int64
 lib.xmve_last_error.argtypes = []
 lib.xmve_last_error.restype = C.c_char_p
 
 #: number of kernel launches issued through this binding (bench.py reports it as gpu_launches)
 launch_count = 0
 _LAUNCHES = {"xmve_prepare_rows": 1, "xmve_score_store": 1, "xmve_score_filter": 1, "xmve_row_kth": 1,
-             "xmve_rescore": 1, "xmve_select_topk_i32": 1, "xmve_select_topk_i64": 1, "xmve_row_topj": 1, "xmve_normalize_f64": 1,
+             "xmve_rescore": 1, "xmve_pilot_top": 1, "xmve_pilot_bound": 1, "xmve_eps_bound": 1, "xmve_merge_topk_packed": 1, "xmve_select_topk_i32": 1, "xmve_select_topk_i64": 1, "xmve_row_topj": 1, "xmve_normalize_f64": 1,
              "xmve_score_f64": 1, "xmve_pairwise_f64": 1, "xmve_gt_ranks": 1, "xmve_rank_metrics": 1, "xmve_list_ranks": 1, "xmve_norm_score": 3, "xmve_fuse_accumulate": 1}
 
 

@@ -37,7 +37,7 @@ rescore_kernel(const float* __restrict__ q_raw, int64_t nq, int64_t q_ld, const 
                const float* __restrict__ v_raw, int64_t nv, int64_t v_ld, const double* __restrict__ v_norm,
                const __grid_constant__ SpaceDesc sp, int norm_mode, const float* __restrict__ cand_score,
                const int32_t* __restrict__ cand_idx, const int32_t* __restrict__ cand_count, int cap,
-               const float* __restrict__ bound, double* __restrict__ exact) {
+               const float* __restrict__ bound, const float* __restrict__ bound_hi, double* __restrict__ exact) {
   extern __shared__ __align__(16) double q_s[];
   const int64_t q = blockIdx.x;
   const int dtot = sp.off[sp.n_space];
@@ -47,14 +47,17 @@ rescore_kernel(const float* __restrict__ q_raw, int64_t nq, int64_t q_ld, const 
   for (int i = threadIdx.x; i < dtot; i += blockDim.x) q_s[i] = static_cast<double>(q_raw[q * q_ld + i]);
   __syncthreads();
   const float bnd = bound ? bound[q] : -CUDART_INF_F;
+  // second round: slots at or above bound_hi hold the exact scores of the first round and are left alone
+  const float bnd_hi = bound_hi ? bound_hi[q] : CUDART_INF_F;
   const bool vec = (v_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(v_raw) & 15u) == 0);
   // Each warp takes 32 candidate slots at a time: one coalesced read of their approximate scores and rows, a ballot
   // of the ones that reach the bound (about one in ten), then one warp-wide dot product per survivor.
   for (int base = (blockIdx.y * RS_WARPS + warp) * 32; base < n; base += gridDim.y * RS_WARPS * 32) {
     const int c = base + lane;                                   // slots >= n are never read downstream
-    const bool mine = c < n && cand_score[q * cap + c] >= bnd;
+    const float approx = c < n ? cand_score[q * cap + c] : -CUDART_INF_F;
+    const bool mine = c < n && approx >= bnd && approx < bnd_hi;
     const int64_t my_v = mine ? cand_idx[q * cap + c] : 0;
-    if (c < n && !mine) exact[q * cap + c] = -CUDART_INF;
+    if (c < n && approx < bnd) exact[q * cap + c] = -CUDART_INF;
     unsigned todo = __ballot_sync(0xffffffffu, mine);
     while (todo != 0) {
       const int src = __ffs(todo) - 1;
@@ -280,8 +283,8 @@ extern "C" int xmve_pairwise_f64(const double* a, int64_t nq, int64_t a_ld, cons
 extern "C" int xmve_rescore(const float* q_raw, int64_t nq, int64_t q_ld, const double* q_norm, const float* v_raw,
                             int64_t nv, int64_t v_ld, const double* v_norm, int n_space, const int32_t* space_off,
                             const double* weights, int norm_mode, const float* cand_score, const int32_t* cand_idx,
-                            const int32_t* cand_count, int32_t cap, const float* bound, double* exact,
-                            void* stream) {
+                            const int32_t* cand_count, int32_t cap, const float* bound, const float* bound_hi,
+                            double* exact, void* stream) {
   using namespace xmve;
   XMVE_DEVICE_OR_RETURN();
   XMVE_REQUIRE(q_raw && q_norm && v_raw && v_norm && space_off && weights && cand_score && cand_idx && cand_count &&
@@ -308,7 +311,7 @@ extern "C" int xmve_rescore(const float* q_raw, int64_t nq, int64_t q_ld, const 
   const dim3 grid(static_cast<unsigned>(nq), static_cast<unsigned>(split));
   rescore_kernel<<<grid, RS_WARPS * 32, dtot * sizeof(double), static_cast<cudaStream_t>(stream)>>>(
       q_raw, nq, q_ld, q_norm, v_raw, nv, v_ld, v_norm, sp, norm_mode, cand_score, cand_idx, cand_count, cap, bound,
-      exact);
+      bound_hi, exact);
   return launch_status("rescore_kernel");
 }
 

@@ -59,13 +59,14 @@ __device__ float block_kth_largest(const float* __restrict__ vals, int64_t n, in
 
 __global__ void __launch_bounds__(256)
 row_kth_kernel(const float* __restrict__ vals, int64_t cols, int64_t ld, const int32_t* __restrict__ counts,
-               int j1, float sub, int j2, float* __restrict__ out) {
+               int j1, float sub, const float* __restrict__ sub_dev, int j2, float* __restrict__ out) {
   __shared__ uint32_t hist[256];
   __shared__ uint32_t bcast[2];
   const int64_t r = blockIdx.x;
   int64_t n = cols;
   if (counts != nullptr) n = min(static_cast<int64_t>(counts[r]), cols);
   const float* row = vals + r * ld;
+  if (sub_dev != nullptr) sub *= sub_dev[0];
   float res = block_kth_largest(row, n, j1, hist, bcast) - sub;
   if (j2 > 0) res = fmaxf(res, block_kth_largest(row, n, j2, hist, bcast));
   if (threadIdx.x == 0) out[r] = res;
@@ -132,13 +133,21 @@ struct IdxLimits<int64_t> {
   static __device__ int64_t max() { return 0x7fffffffffffffffLL; }
 };
 
+// Segmented input of the selection kernel (K3 after ONE all-gather of packed per-rank blocks): n segments, each a
+// [rows, len] block `stride` elements after the previous one; overflow flags [rows] per segment, flag_stride apart.
+struct Segments {
+  int n;
+  int64_t len, stride, flag_stride;
+};
+
 template <typename IdxT>
 __global__ void __launch_bounds__(512)
 select_topk_kernel(const double* __restrict__ score, const IdxT* __restrict__ idx, int64_t cols,
                    const int32_t* __restrict__ counts, int64_t idx_offset, const int64_t* __restrict__ exclude, int k,
-                   const float* __restrict__ thr, float eps, const float* __restrict__ bound,
-                   const int32_t* __restrict__ overflow, int pmax, double* __restrict__ out_score, int64_t* __restrict__ out_idx, int32_t* __restrict__ out_valid,
-                   int32_t* __restrict__ cert, float* __restrict__ thr_next) {
+                   const float* __restrict__ thr, float eps, const float* __restrict__ eps_dev,
+                   const float* __restrict__ bound, const int32_t* __restrict__ overflow, Segments seg, int pmax,
+                   double* __restrict__ out_score, int64_t* __restrict__ out_idx, int32_t* __restrict__ out_valid,
+                   int32_t* __restrict__ cert, float* __restrict__ thr_next, int32_t* __restrict__ n_uncertified) {
   extern __shared__ __align__(16) uint8_t sel_smem[];
   double* keys = reinterpret_cast<double*>(sel_smem);
   IdxT* ids = reinterpret_cast<IdxT*>(keys + pmax);
@@ -150,18 +159,26 @@ select_topk_kernel(const double* __restrict__ score, const IdxT* __restrict__ id
     cand_overflow = counts[r] > cols;
     n_in = min(static_cast<int64_t>(counts[r]), cols);
   }
-  if (overflow != nullptr && overflow[r] != 0) cand_overflow = true;   // a shard's candidate list overflowed
+  if (eps_dev != nullptr) eps *= eps_dev[0];
+  if (overflow != nullptr)                                             // a shard's candidate list overflowed
+    for (int g = 0; g < seg.n; ++g)
+      if (overflow[g * seg.flag_stride + r] != 0) cand_overflow = true;
   __shared__ uint32_t sel_hist[256];
   __shared__ uint32_t sel_bcast[2];
   if (threadIdx.x == 0) n_valid_s = 0;
   __syncthreads();
   const int64_t excl = exclude ? exclude[r] : -1;
-  const double* srow = score + r * cols;
-  const IdxT* irow = idx ? idx + r * cols : nullptr;
+  // entry i of row r: contiguous [rows, cols], or (segmented) the per-rank blocks of an all-gathered buffer --
+  // segment g = i / seg.len holds its [rows, seg.len] block at g * seg.stride elements
+  auto at = [&](int64_t i) -> int64_t {
+    if (seg.n <= 1) return r * cols + i;
+    const int64_t g = i / seg.len;
+    return g * seg.stride + r * seg.len + (i - g * seg.len);
+  };
   // valid entry i -> its score, anything else -> -inf
   auto value = [&](int64_t i) -> double {
-    const double s = srow[i];
-    const IdxT id = irow ? irow[i] : static_cast<IdxT>(i);            // idx == NULL: column number
+    const double s = score[at(i)];
+    const IdxT id = idx ? idx[at(i)] : static_cast<IdxT>(i);          // idx == NULL: column number
     return (s > -CUDART_INF && !(exclude && static_cast<int64_t>(id) + idx_offset == excl)) ? s : -CUDART_INF;
   };
   for (int64_t i = threadIdx.x; i < n_in; i += blockDim.x)
@@ -184,7 +201,7 @@ select_topk_kernel(const double* __restrict__ score, const IdxT* __restrict__ id
       const int pos = atomicAdd(&n_valid_s, 1);
       if (pos < pmax) {
         keys[pos] = s;
-        ids[pos] = irow ? irow[i] : static_cast<IdxT>(i);
+        ids[pos] = idx ? idx[at(i)] : static_cast<IdxT>(i);
       }
     }
   }
@@ -229,6 +246,7 @@ select_topk_kernel(const double* __restrict__ score, const IdxT* __restrict__ id
       const double kth = enough ? keys[k - 1] : -CUDART_INF;
       const bool complete = (t == -CUDART_INF_F) || (kth - static_cast<double>(eps) >= static_cast<double>(t));
       cert[r] = (!cand_overflow && enough && complete) ? 1 : 0;
+      if (n_uncertified != nullptr && cert[r] == 0) atomicAdd(n_uncertified, 1);
       if (thr_next != nullptr) {
         float nx;
         if (cand_overflow || n_valid > pmax) nx = bound ? bound[r] : t;          // approx kth of retained - 2 eps
@@ -237,6 +255,123 @@ select_topk_kernel(const double* __restrict__ score, const IdxT* __restrict__ id
         thr_next[r] = nx;
       }
     }
+  }
+}
+
+// ---- two-round rescore: the pilot ------------------------------------------------------------------
+// Round one rescores each shard's m best approximate candidates exactly.  pilot_top extracts the (up to) m largest
+// of those exact scores per row, descending, -inf padded (the entry of the query's excluded item is skipped); the
+// lists of all shards are gathered and pilot_bound turns the k-th largest exact score of the union -- a LOWER bound
+// on the true k-th best score, whatever subset was rescored -- into the second-round window: a candidate whose
+// approximate score is below kth1 - eps cannot reach the top-k (exact <= approx + eps < kth1 <= true k-th).
+constexpr int PILOT_MAX = 1024;
+
+__global__ void __launch_bounds__(256)
+pilot_top_kernel(const double* __restrict__ exact, const int32_t* __restrict__ idx, const int32_t* __restrict__ counts,
+                 int cap, int64_t idx_offset, const int64_t* __restrict__ exclude, int m, double* __restrict__ out) {
+  __shared__ double buf[PILOT_MAX];
+  __shared__ int n_s;
+  const int64_t r = blockIdx.x;
+  const int n_in = min(counts[r], cap);
+  const int64_t excl = exclude ? exclude[r] : -1;
+  if (threadIdx.x == 0) n_s = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_in; i += blockDim.x) {
+    const double s = exact[r * cap + i];
+    if (s > -CUDART_INF && !(exclude && static_cast<int64_t>(idx[r * cap + i]) + idx_offset == excl)) {
+      const int pos = atomicAdd(&n_s, 1);
+      if (pos < PILOT_MAX) buf[pos] = s;          // more than PILOT_MAX (ties at the round-one bound): any subset is valid
+    }
+  }
+  __syncthreads();
+  const int n = min(n_s, PILOT_MAX);
+  int P = 1;
+  while (P < n) P <<= 1;
+  for (int i = n + threadIdx.x; i < P; i += blockDim.x) buf[i] = -CUDART_INF;
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < P; t += blockDim.x) {
+        const int o = t ^ stride;
+        if (o > t) {
+          const bool desc = (t & size) == 0;
+          const double a = buf[t], b = buf[o];
+          if (desc ? (b > a) : (a > b)) { buf[t] = b; buf[o] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < m; i += blockDim.x) out[r * m + i] = i < n ? buf[i] : -CUDART_INF;
+}
+
+// lists [n_seg, rows, m] (descending per segment) -> bound[r] = round_down(kth largest of the union - eps), -inf when
+// the union holds fewer than k finite scores.  One warp per row: rank of every element by counting.
+__global__ void __launch_bounds__(256)
+pilot_bound_kernel(const double* __restrict__ lists, int n_seg, int64_t rows, int m, int k, float eps,
+                   const float* __restrict__ eps_dev, float* __restrict__ bound) {
+  const int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  if (eps_dev != nullptr) eps *= eps_dev[0];
+  const int total = n_seg * m;
+  // the k-th largest value x: #{y > x} < k <= #{y >= x}
+  double kth = -CUDART_INF;
+  for (int base = 0; base < total; base += 32) {
+    const int i = base + lane;
+    double x = -CUDART_INF;
+    if (i < total) x = lists[(static_cast<int64_t>(i / m) * rows + r) * m + (i % m)];
+    int gt = 0, ge = 0;
+    for (int g = 0; g < n_seg; ++g) {
+      const double* seg = lists + (static_cast<int64_t>(g) * rows + r) * m;
+      // descending segment: binary search for the counts
+      int lo = 0, hi = m;                                      // first position with seg[p] <= x  -> #{y > x}
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (seg[mid] > x) lo = mid + 1; else hi = mid; }
+      gt += lo;
+      hi = m;                                                  // first position with seg[p] < x   -> #{y >= x}
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (seg[mid] >= x) lo = mid + 1; else hi = mid; }
+      ge += lo;
+    }
+    if (x > -CUDART_INF && gt < k && k <= ge) kth = x;
+    if (__any_sync(0xffffffffu, kth > -CUDART_INF)) break;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kth = fmax(kth, __shfl_xor_sync(0xffffffffu, kth, o));
+  if (lane == 0) bound[r] = kth > -CUDART_INF ? __double2float_rd(kth - static_cast<double>(eps)) : -CUDART_INF_F;
+}
+
+// ---- the error bound eps on the device (engine.measured_eps without a host round trip) ---------------------------
+// dq2 = max over queries of sum_s q_resid[s][q]; eps = dq*vn + qn*dv + k_len*2^-22*qn*vn + 1e-6 with
+// qn = sqrt(sum w^2) + dq, vn = sqrt(S)*(1 + 2^-8); NaN / non-positive -> fallback.  One block.
+__global__ void __launch_bounds__(1024)
+eps_bound_kernel(const float* __restrict__ q_resid, int n_space, int64_t nq, const float* __restrict__ dv2,
+                 double w_norm, int k_len, float fallback, float* __restrict__ eps_out) {
+  __shared__ float red[32];
+  __shared__ int bad_s;
+  if (threadIdx.x == 0) bad_s = 0;
+  __syncthreads();
+  float mx = 0.f;
+  bool bad = false;
+  for (int64_t q = threadIdx.x; q < nq; q += blockDim.x) {
+    float t = 0.f;
+    for (int s = 0; s < n_space; ++s) t += q_resid[static_cast<int64_t>(s) * nq + q];
+    if (!(t == t)) bad = true;
+    mx = fmaxf(mx, t);
+  }
+  if (bad) bad_s = 1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < static_cast<int>(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+    const float dv2v = dv2[0];
+    double e = -1.0;
+    if (!bad_s && dv2v == dv2v) {
+      const double dq = sqrt(static_cast<double>(mx)), dv = sqrt(static_cast<double>(dv2v));
+      const double qn = w_norm + dq, vn = sqrt(static_cast<double>(n_space)) * (1.0 + 0.00390625);
+      e = dq * vn + qn * dv + static_cast<double>(k_len) * 2.384185791015625e-07 * qn * vn + 1e-6;
+    }
+    eps_out[0] = (e > 0.0 && e < CUDART_INF) ? __double2float_ru(e) : fallback;
   }
 }
 
@@ -249,13 +384,23 @@ int pow2_ceil(int64_t x) {
 template <typename IdxT>
 int launch_select(const double* score, const IdxT* idx, int64_t rows, int64_t cols, const int32_t* counts,
                   int64_t idx_offset, const int64_t* exclude, int32_t k, const float* thr, float eps,
-                  const float* bound, const int32_t* overflow, double* out_score, int64_t* out_idx, int32_t* out_valid,
-                  int32_t* cert, float* thr_next, cudaStream_t st) {
+                  const float* eps_dev, const float* bound, const int32_t* overflow, Segments seg, double* out_score,
+                  int64_t* out_idx, int32_t* out_valid, int32_t* cert, float* thr_next, int32_t* n_uncertified,
+                  cudaStream_t st) {
   XMVE_REQUIRE(score && out_score && out_idx && rows >= 0 && cols > 0 && k > 0, "select_topk: bad arguments");
   XMVE_REQUIRE(cert == nullptr || thr != nullptr, "select_topk: cert needs thr");
   if (rows == 0) return XMVE_OK;
   int pmax = pow2_ceil(cols);
   if (pmax > 16384) pmax = 16384;
+  // Many rows: a modest sort capacity keeps several blocks resident per SM (the full 16384-entry buffer is 196 KB:
+  // one block per SM, 1.7 ms for 8192 rows of ~500 valid entries each).  Rows with more valid entries than the
+  // capacity are first cut at their k-th largest rounded score (see the kernel); the few rows that still do not fit
+  // come back uncertified and are re-run in a small batch, which gets the full capacity.
+  if (rows >= 512) {
+    int small = pow2_ceil(4 * static_cast<int64_t>(k));
+    if (small < 2048) small = 2048;
+    if (pmax > small) pmax = small;
+  }
   if (pmax < k) return fail(XMVE_ERR_LIMIT, "select_topk: k=%d exceeds the %d-entry sort capacity", k, pmax);
   const int smem = pmax * static_cast<int>(sizeof(double) + sizeof(IdxT));
   if (smem > 220 * 1024) {
@@ -271,8 +416,8 @@ int launch_select(const double* score, const IdxT* idx, int64_t rows, int64_t co
     attr_bytes[dev] = smem_bytes;
   }
   select_topk_kernel<IdxT><<<static_cast<unsigned>(rows), 512, smem_bytes, st>>>(
-      score, idx, cols, counts, idx_offset, exclude, k, thr, eps, bound, overflow, pmax, out_score, out_idx, out_valid,
-      cert, thr_next);
+      score, idx, cols, counts, idx_offset, exclude, k, thr, eps, eps_dev, bound, overflow, seg, pmax, out_score,
+      out_idx, out_valid, cert, thr_next, n_uncertified);
   return launch_status("select_topk_kernel");
 }
 
@@ -280,35 +425,62 @@ int launch_select(const double* score, const IdxT* idx, int64_t rows, int64_t co
 }  // namespace xmve
 
 extern "C" int xmve_row_kth(const float* vals, int64_t rows, int64_t cols, int64_t ld, const int32_t* counts,
-                            int32_t j1, float sub, int32_t j2, float* out, void* stream) {
+                            int32_t j1, float sub, const float* sub_dev, int32_t j2, float* out, void* stream) {
   using namespace xmve;
   XMVE_DEVICE_OR_RETURN();
   XMVE_REQUIRE(vals && out && rows >= 0 && cols > 0 && ld >= cols && j1 > 0, "row_kth: bad arguments");
   if (rows == 0) return XMVE_OK;
   row_kth_kernel<<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(vals, cols, ld, counts,
-                                                                                            j1, sub, j2, out);
+                                                                                            j1, sub, sub_dev, j2, out);
   return launch_status("row_kth_kernel");
 }
 
 extern "C" int xmve_select_topk_i32(const double* score, const int32_t* idx, int64_t rows, int64_t cols,
                                     const int32_t* counts, int64_t idx_offset, const int64_t* exclude, int32_t k,
-                                    const float* thr, float eps, const float* bound, double* out_score,
-                                    int64_t* out_idx, int32_t* out_valid, int32_t* cert, float* thr_next,
-                                    void* stream) {
+                                    const float* thr, float eps, const float* eps_dev, const float* bound,
+                                    double* out_score, int64_t* out_idx, int32_t* out_valid, int32_t* cert,
+                                    float* thr_next, int32_t* n_uncertified, void* stream) {
   using namespace xmve;
   XMVE_DEVICE_OR_RETURN();
-  return launch_select<int32_t>(score, idx, rows, cols, counts, idx_offset, exclude, k, thr, eps, bound, nullptr,
-                                out_score, out_idx, out_valid, cert, thr_next, static_cast<cudaStream_t>(stream));
+  return launch_select<int32_t>(score, idx, rows, cols, counts, idx_offset, exclude, k, thr, eps, eps_dev, bound,
+                                nullptr, Segments{1, cols, 0, 0}, out_score, out_idx, out_valid, cert, thr_next,
+                                n_uncertified, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int xmve_select_topk_i64(const double* score, const int64_t* idx, int64_t rows, int64_t cols,
                                     const int64_t* exclude, int32_t k, const float* thr, float eps,
-                                    const int32_t* overflow, double* out_score, int64_t* out_idx, int32_t* out_valid,
-                                    int32_t* cert, float* thr_next, void* stream) {
+                                    const float* eps_dev, const int32_t* overflow, double* out_score, int64_t* out_idx,
+                                    int32_t* out_valid, int32_t* cert, float* thr_next, int32_t* n_uncertified,
+                                    void* stream) {
   using namespace xmve;
   XMVE_DEVICE_OR_RETURN();
-  return launch_select<int64_t>(score, idx, rows, cols, nullptr, 0, exclude, k, thr, eps, nullptr, overflow, out_score,
-                                out_idx, out_valid, cert, thr_next, static_cast<cudaStream_t>(stream));
+  return launch_select<int64_t>(score, idx, rows, cols, nullptr, 0, exclude, k, thr, eps, eps_dev, nullptr, overflow,
+                                Segments{1, cols, 0, rows}, out_score, out_idx, out_valid, cert, thr_next,
+                                n_uncertified, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int xmve_merge_topk_packed(const void* packed, int32_t n_seg, int64_t seg_bytes, int64_t rows, int32_t len,
+                                      const int64_t* exclude, int32_t k, const float* thr, float eps,
+                                      const float* eps_dev, double* out_score, int64_t* out_idx, int32_t* cert,
+                                      float* thr_next, int32_t* n_uncertified, void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  XMVE_REQUIRE(packed != nullptr && n_seg >= 1 && rows >= 0 && len > 0, "merge_topk_packed: bad arguments");
+  const int64_t need = xmve_packed_topk_bytes(rows, len);
+  XMVE_REQUIRE(seg_bytes >= need && seg_bytes % 8 == 0, "merge_topk_packed: seg_bytes %lld < %lld or not a multiple of 8",
+               static_cast<long long>(seg_bytes), static_cast<long long>(need));
+  const uint8_t* base = static_cast<const uint8_t*>(packed);
+  const double* score = reinterpret_cast<const double*>(base);
+  const int64_t* idx = reinterpret_cast<const int64_t*>(base + rows * len * 8);
+  const int32_t* flags = reinterpret_cast<const int32_t*>(base + rows * len * 16);
+  return launch_select<int64_t>(score, idx, rows, static_cast<int64_t>(n_seg) * len, nullptr, 0, exclude, k, thr, eps,
+                                eps_dev, nullptr, flags, Segments{n_seg, len, seg_bytes / 8, seg_bytes / 4}, out_score,
+                                out_idx, nullptr, cert, thr_next, n_uncertified, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int64_t xmve_packed_topk_bytes(int64_t rows, int32_t len) {
+  const int64_t b = rows * len * 16 + rows * 4;
+  return (b + 15) / 16 * 16;
 }
 
 extern "C" int xmve_row_topj(const float* vals, int64_t rows, int64_t cols, int64_t ld, const int32_t* counts,
@@ -322,4 +494,38 @@ extern "C" int xmve_row_topj(const float* vals, int64_t rows, int64_t cols, int6
   row_topj_kernel<<<static_cast<unsigned>(rows), 256, P * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       vals, cols, ld, counts, j, P, out);
   return launch_status("row_topj_kernel");
+}
+
+extern "C" int xmve_pilot_top(const double* exact, const int32_t* idx, const int32_t* counts, int64_t rows, int32_t cap,
+                              int64_t idx_offset, const int64_t* exclude, int32_t m, double* out, void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  XMVE_REQUIRE(exact && idx && counts && out && rows >= 0 && cap > 0 && m > 0, "pilot_top: bad arguments");
+  if (m > PILOT_MAX) return fail(XMVE_ERR_LIMIT, "pilot_top: m=%d exceeds %d", m, PILOT_MAX);
+  if (rows == 0) return XMVE_OK;
+  pilot_top_kernel<<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      exact, idx, counts, cap, idx_offset, exclude, m, out);
+  return launch_status("pilot_top_kernel");
+}
+
+extern "C" int xmve_pilot_bound(const double* lists, int32_t n_seg, int64_t rows, int32_t m, int32_t k, float eps,
+                                const float* eps_dev, float* bound, void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  XMVE_REQUIRE(lists && bound && n_seg >= 1 && rows >= 0 && m > 0 && k > 0, "pilot_bound: bad arguments");
+  if (rows == 0) return XMVE_OK;
+  const int64_t blocks = (rows + 7) / 8;
+  pilot_bound_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      lists, n_seg, rows, m, k, eps, eps_dev, bound);
+  return launch_status("pilot_bound_kernel");
+}
+
+extern "C" int xmve_eps_bound(const float* q_resid, int32_t n_space, int64_t nq, const float* dv2, double w_norm,
+                              int32_t k_len, float fallback, float* eps_out, void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  XMVE_REQUIRE(q_resid && dv2 && eps_out && n_space >= 1 && nq >= 0 && k_len > 0, "eps_bound: bad arguments");
+  eps_bound_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(q_resid, n_space, nq, dv2, w_norm, k_len,
+                                                                      fallback, eps_out);
+  return launch_status("eps_bound_kernel");
 }

@@ -2,9 +2,11 @@
 
 Every rank runs the search pipeline on its own shard against ONE global per-query threshold
 (``engine.search_shards``): two small ``all_gather`` s of per-shard order statistics (the top-J sample scores,
-then the top-k approximate candidate scores; ~2-3 MB per rank at 8192 queries) make every shard append and
-rescore only its share of the candidates, and one ``all_gather`` of the ``[nq, k]`` exact (score, index) lists
-over NCCL / NVLink followed by the G-way merge kernel (K3) gives every rank the certified global top-k.  Exact
+then the exact scores of every shard's best few candidates -- the pilot of the two-round rescore; ~2-3 MB per rank
+at 8192 queries) make every shard append and rescore only its share of the candidates, and ONE ``all_gather`` of a
+packed block per rank (``[nq, k]`` exact scores, global rows, overflow flags) over NCCL / NVLink followed by the
+G-way merge kernel (K3) gives every rank the certified global top-k.  No collective needs the host: the error
+bound lives on the device and the certificate is read back asynchronously.  Exact
 fp64 scores are comparable across shards, so the merge is exact.  The reference has no multi-GPU path for this
 stage; this is the design of section 8e.
 """
@@ -29,10 +31,12 @@ class GroupComm:
         self.world = dist.get_world_size(group)
 
     def gather(self, t):
-        """``t`` (same shape on every rank) -> ``[world, *t.shape]`` on every rank."""
-        parts = [torch.empty_like(t) for _ in range(self.world)]
-        dist.all_gather(parts, t.contiguous(), group=self.group)
-        return torch.stack(parts)
+        """``t`` (same shape on every rank) -> ``[world, *t.shape]`` on every rank: ONE collective straight into the
+        result (no per-rank list, no ``torch.stack`` copy)."""
+        t = t.contiguous()
+        out = torch.empty((self.world * t.numel(),), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.reshape(-1), group=self.group)
+        return out.view((self.world,) + tuple(t.shape))
 
     def max_(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)

@@ -8,8 +8,10 @@ Replaces, for a corpus that is encoded once and queried many times, the per-call
 
 The pipeline is :func:`search_shards` (its docstring lists the steps): K1 on the queries, a sampled per-query
 threshold, the fused tcgen05 score + threshold filter over the resident operand (the score matrix never reaches
-HBM), an exact fp64 rescore of the survivors, a bitonic top-k with a certificate that nothing outside the
-candidate set can belong to the top-k, and a re-run of the rare rows that miss the certificate.
+HBM), an exact fp64 rescore of the survivors in two rounds, a bitonic top-k with a certificate that nothing
+outside the candidate set can belong to the top-k, and a re-run of the rare rows that miss the certificate.
+The first pass never waits for the host: the error bound is a device scalar, the number of uncertified rows comes
+back through one asynchronous copy (``defer=True`` hands the caller a :class:`PendingSearch` to resolve later).
 :meth:`CorpusStore.search` is the one-shard case; ``distributed.sharded_search`` joins the shards of several GPUs.
 """
 from __future__ import annotations
@@ -27,6 +29,7 @@ from . import _native as N
 #: (search(eps=...) callers, NaN rows); the search itself uses :func:`measured_eps` (typically 3.5e-3 - 4e-3).
 EPS_X1 = 8.5e-3
 SMALL_NV = 16384
+ROW_TOPJ_MAX = 4096
 _BM, _BN = 128, 256
 
 
@@ -86,11 +89,23 @@ class CorpusStore:
     with :meth:`add` (the analogue of ``encode_vid``'s batch loop, evaluation.py:98-105) and
     normalised once, on the device, as they arrive.  ``index_offset`` is this shard's first global
     row (multi-GPU sharding).
+
+    Memory: ``capacity * (2 * sum(dpad) + 4 * sum(dims) + 12 * S)`` bytes -- 12.3 KB per row at 1536 + 512 dims, i.e.
+    123 GB for the 10 M-row C5 corpus (41 GB bf16 operand + 82 GB fp32 raw rows kept for the exact rescore) and a
+    ceiling of about 14 M such rows per 180 GB B200; larger corpora are sharded (``distributed.shard_range``).  The
+    constructor checks the free device memory first and raises a sized ``MemoryError`` instead of a CUDA OOM.
+
+    Inputs are taken as the reference keeps them: fp32 model outputs, possibly stored in float64 arrays
+    (evaluation.py:102-105).  float64 inputs are therefore narrowed to fp32 by K1 (exact for such arrays); the
+    fp64 arithmetic of the rescore then equals ``cal_error`` on the float64 copies.  Genuinely double-precision
+    embeddings would be ranked after rounding to fp32 -- use ``evaluation.cal_error`` for those.
     """
 
     def __init__(self, capacity, dims, device="cuda", norm_mode="plain", index_offset=0):
         N.require_device()
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.dims = tuple(int(d) for d in (dims if isinstance(dims, (list, tuple)) else (dims,)))
         self.dpads = tuple(_round_up(d, 64) for d in self.dims)
         self.k = sum(self.dpads)
@@ -101,6 +116,14 @@ class CorpusStore:
         self.index_offset = int(index_offset)
         self.n = 0
         rows = _round_up(max(self.capacity, 1), _BN)
+        need = rows * self.k * 2 + max(self.capacity, 1) * (self.raw_ld * 4 + len(self.dims) * 12)
+        free = torch.cuda.mem_get_info(self.device)[0] + torch.cuda.memory_reserved(self.device) \
+            - torch.cuda.memory_allocated(self.device)
+        if need > free:
+            raise MemoryError(
+                "CorpusStore: %d rows x %s dims need %.1f GB of HBM (bf16 operand + fp32 raw rows + norms) but only "
+                "%.1f GB are free on %s; shard the corpus over more GPUs (distributed.shard_range) or lower the "
+                "capacity" % (self.capacity, list(self.dims), need / 1e9, free / 1e9, self.device))
         self.op = torch.zeros((rows, self.k), dtype=torch.bfloat16, device=self.device)
         self.raw = torch.empty((max(self.capacity, 1), self.raw_ld), dtype=torch.float32, device=self.device)
         self.norm = torch.empty((len(self.dims), max(self.capacity, 1)), dtype=torch.float64, device=self.device)
@@ -116,12 +139,13 @@ class CorpusStore:
         if self.n + n > self.capacity:
             raise ValueError("CorpusStore capacity %d exceeded" % self.capacity)
         op_off = raw_off = 0
-        for s, (src, d, dp) in enumerate(zip(spaces, self.dims, self.dpads)):
-            assert src.shape[-1] == d, "space %d: expected dim %d, got %d" % (s, d, src.shape[-1])
-            _prepare(src, d, self.raw[self.n:], raw_off, self.norm[s, self.n:], self.resid[s, self.n:],
-                     self.op[self.n:], op_off, N.OP_X1, 1.0, self.norm_mode)
-            op_off += dp
-            raw_off += d
+        with torch.cuda.device(self.device):                  # launch on the store's device, whatever is current
+            for s, (src, d, dp) in enumerate(zip(spaces, self.dims, self.dpads)):
+                assert src.shape[-1] == d, "space %d: expected dim %d, got %d" % (s, d, src.shape[-1])
+                _prepare(src, d, self.raw[self.n:], raw_off, self.norm[s, self.n:], self.resid[s, self.n:],
+                         self.op[self.n:], op_off, N.OP_X1, 1.0, self.norm_mode)
+                op_off += dp
+                raw_off += d
         self.n += n
         return self
 
@@ -144,17 +168,18 @@ class CorpusStore:
         return a_op, q_raw, q_norm, q_res, nq
 
     # -- search ----------------------------------------------------------------------------------
-    def search(self, queries, k, weights=None, exclude=None, eps=None, small_nv=SMALL_NV, stats=None):
+    def search(self, queries, k, weights=None, exclude=None, eps=None, small_nv=SMALL_NV, stats=None, defer=False):
         """Top-``k`` corpus rows per query by fused cosine score, exact (fp64) scores, descending.
 
         Returns ``(scores float64 [nq, k], idx int64 [nq, k])`` on the device; ``idx`` are global row
         numbers (``index_offset`` + local), ``-1`` / ``-inf`` padded if the corpus has fewer than ``k``
         rows.  ``exclude[q]`` (global row or -1) is dropped from row q's list -- MultiFusion's removal
         of the query's own reference item (validate.py:76-83).  ``eps`` overrides the measured bound on
-        |tensor-core score - exact score| (see :func:`measured_eps`).
+        |tensor-core score - exact score| (see :func:`measured_eps`).  ``defer=True`` returns a
+        :class:`PendingSearch` as soon as the work is enqueued (``.result()`` gives the tuple).
         """
         return search_shards([self], queries, k, weights=weights, exclude=exclude, eps=eps, small_nv=small_nv,
-                             stats=stats)
+                             stats=stats, defer=defer)
 
     def plan(self, k, n=None):
         return plan(k, self.n if n is None else n)
@@ -194,7 +219,7 @@ class CorpusStore:
         s_ = torch.empty((nq, kk), dtype=torch.float64, device=dev)
         i_ = torch.empty((nq, kk), dtype=torch.int64, device=dev)
         N.call("xmve_select_topk_i32", N.ptr(acc), None, nq, self.n, None, self.index_offset, N.ptr(excl), kk,
-               None, 0.0, None, N.ptr(s_), N.ptr(i_), None, None, None, st)
+               None, 0.0, None, None, N.ptr(s_), N.ptr(i_), None, None, None, None, st)
         out_s[:, :kk] = s_
         out_i[:, :kk] = i_
         return out_s, out_i
@@ -236,26 +261,40 @@ class CorpusStore:
         count, score, _ = self._filter(a_op, nq, thr0, cap_s, step=step)
         return score, count, thr0
 
-    def _rescore_select(self, q_raw, q_norm, nq, k, wts, excl, cand, bound, thr, eps, certify):
-        """Exact fp64 rescore of the candidates above ``bound`` + local top-k (global row ids)."""
-        dev, st = self.device, N.stream_ptr()
+    def _rescore(self, q_raw, q_norm, nq, wts, cand, bound, bound_hi=None, exact=None):
+        """Exact fp64 scores of the candidates whose approximate score reaches ``bound`` (second round: of those in
+        ``[bound, bound_hi)``, the entries at or above ``bound_hi`` keep their first-round values) -> fp64 [nq, cap]."""
         cand_count, cand_score, cand_idx = cand
         cap = cand_score.shape[1]
-        exact = torch.empty((nq, cap), dtype=torch.float64, device=dev)
+        if exact is None:
+            exact = torch.empty((nq, cap), dtype=torch.float64, device=self.device)
         N.call("xmve_rescore", N.ptr(q_raw), nq, q_raw.stride(0), N.ptr(q_norm), N.ptr(self.raw), self.n,
                self.raw.stride(0), N.ptr(self.norm), len(self.dims), self.space_off, self._weights_arr(wts),
                self.norm_mode, N.ptr(cand_score), N.ptr(cand_idx), N.ptr(cand_count), cap, N.ptr(bound),
-               N.ptr(exact), st)
-        out_s = torch.empty((nq, k), dtype=torch.float64, device=dev)
-        out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+               N.ptr(bound_hi), N.ptr(exact), N.stream_ptr())
+        return exact
+
+    def _pilot_top(self, exact, cand, nq, excl, m):
+        """The ``m`` largest first-round exact scores per query, descending, -inf padded -> fp64 [nq, m]."""
+        cand_count, cand_score, cand_idx = cand
+        out = torch.empty((nq, m), dtype=torch.float64, device=self.device)
+        N.call("xmve_pilot_top", N.ptr(exact), N.ptr(cand_idx), N.ptr(cand_count), nq, cand_score.shape[1],
+               self.index_offset, N.ptr(excl), m, N.ptr(out), N.stream_ptr())
+        return out
+
+    def _select(self, exact, cand, nq, k, excl, thr, eps_t, bound, out_s, out_i, certify, n_bad=None):
+        """Local top-k (global row ids) of the rescored candidates into ``out_s`` / ``out_i`` (+ certificate)."""
+        cand_count, cand_score, cand_idx = cand
+        cap = cand_score.shape[1]
         cert = thr_next = None
         if certify:
-            cert = torch.empty((nq,), dtype=torch.int32, device=dev)
-            thr_next = torch.empty((nq,), dtype=torch.float32, device=dev)
+            cert = torch.empty((nq,), dtype=torch.int32, device=self.device)
+            thr_next = torch.empty((nq,), dtype=torch.float32, device=self.device)
         N.call("xmve_select_topk_i32", N.ptr(exact), N.ptr(cand_idx), nq, cap, N.ptr(cand_count),
-               self.index_offset, N.ptr(excl), k, N.ptr(thr) if certify else None, float(eps),
-               N.ptr(bound) if certify else None, N.ptr(out_s), N.ptr(out_i), None, N.ptr(cert), N.ptr(thr_next), st)
-        return out_s, out_i, cert, thr_next
+               self.index_offset, N.ptr(excl), k, N.ptr(thr) if certify else None, 1.0, N.ptr(eps_t),
+               N.ptr(bound) if certify else None, N.ptr(out_s), N.ptr(out_i), None, N.ptr(cert), N.ptr(thr_next),
+               N.ptr(n_bad) if certify else None, N.stream_ptr())
+        return cert, thr_next
 
 
 def plan(k, n):
@@ -334,13 +373,57 @@ def _row_topj(vals, counts, j):
     return out
 
 
-def _row_kth(vals, counts, j1, sub, j2):
+def _row_kth(vals, counts, j1, sub, j2, sub_dev=None):
+    """``max(kth(row, j1) - sub * sub_dev[0], kth(row, j2))`` per row (``sub_dev`` None: ``- sub``)."""
     rows, cols = vals.shape
     out = torch.empty((rows,), dtype=torch.float32, device=vals.device)
     if rows:
-        N.call("xmve_row_kth", N.ptr(vals), rows, cols, vals.stride(0), N.ptr(counts), j1, float(sub), j2, N.ptr(out),
-               N.stream_ptr())
+        N.call("xmve_row_kth", N.ptr(vals), rows, cols, vals.stride(0), N.ptr(counts), j1, float(sub), N.ptr(sub_dev), j2,
+               N.ptr(out), N.stream_ptr())
     return out
+
+
+def _eps_device(q_res, dv2, wts, n_space, k_len):
+    """:func:`measured_eps` on the device: fp32 ``[1]`` tensor (no host round trip)."""
+    out = torch.empty((1,), dtype=torch.float32, device=q_res.device)
+    N.call("xmve_eps_bound", N.ptr(q_res), n_space, q_res.shape[1], N.ptr(dv2), math.sqrt(sum(w * w for w in wts)),
+           int(k_len), EPS_X1 * max(1.0, sum(abs(w) for w in wts)), N.ptr(out), N.stream_ptr())
+    return out
+
+
+def _pilot_bound(lists, k, eps_t):
+    """``lists`` fp64 ``[n_seg, nq, m]`` (descending per segment) -> round_down(k-th largest of the union - eps)."""
+    n_seg, nq, m = lists.shape
+    out = torch.empty((nq,), dtype=torch.float32, device=lists.device)
+    if nq:
+        N.call("xmve_pilot_bound", N.ptr(lists), n_seg, nq, m, k, 1.0, N.ptr(eps_t), N.ptr(out), N.stream_ptr())
+    return out
+
+
+def packed_bytes(rows, length):
+    """Bytes of one packed top-k block: scores fp64 [rows, len] | rows int64 [rows, len] | overflow int32 [rows]."""
+    return int(N.lib.xmve_packed_topk_bytes(int(rows), int(length)))
+
+
+def packed_views(block, rows, length):
+    """Typed views (scores, idx, flags) into one packed block (a uint8 tensor of :func:`packed_bytes` bytes)."""
+    n = rows * length
+    return (block[: n * 8].view(torch.float64).view(rows, length),
+            block[n * 8: n * 16].view(torch.int64).view(rows, length),
+            block[n * 16: n * 16 + rows * 4].view(torch.int32))
+
+
+def _merge_packed(packed, rows, length, k, thr, eps_t, n_bad):
+    """K3 on the all-gathered packed blocks ``[n_seg, seg_bytes]`` -> (scores, idx, cert, thr_next)."""
+    n_seg, seg_bytes = packed.shape
+    out_s = torch.empty((rows, k), dtype=torch.float64, device=packed.device)
+    out_i = torch.empty((rows, k), dtype=torch.int64, device=packed.device)
+    cert = torch.empty((rows,), dtype=torch.int32, device=packed.device)
+    thr_next = torch.empty((rows,), dtype=torch.float32, device=packed.device)
+    if rows:
+        N.call("xmve_merge_topk_packed", N.ptr(packed), n_seg, seg_bytes, rows, length, None, k, N.ptr(thr), 1.0,
+               N.ptr(eps_t), N.ptr(out_s), N.ptr(out_i), N.ptr(cert), N.ptr(thr_next), N.ptr(n_bad), N.stream_ptr())
+    return out_s, out_i, cert, thr_next
 
 
 def _union(parts, comm):
@@ -352,27 +435,269 @@ def _union(parts, comm):
     return g.permute(1, 0, 2).reshape(loc.shape[0], -1).contiguous()
 
 
+def _segments(parts, comm):
+    """Per-shard tensors of one shape -> ``[G * L, *shape]`` over all shards of all ranks (one collective)."""
+    loc = parts[0].unsqueeze(0) if len(parts) == 1 else torch.stack(parts)
+    if comm.world == 1:
+        return loc
+    g = comm.gather(loc)                                                # [G, L, ...]
+    return g.view((-1,) + tuple(loc.shape[1:]))
+
+
+#: the pilot holds at most this many exact scores per query and shard (xmve_pilot_top)
+PILOT_MAX = 1000
+
+
+class PendingSearch:
+    """A search whose first pass has been enqueued.  :meth:`result` waits for the count of uncertified rows (one
+    int32 copied asynchronously to pinned host memory right after the merge), re-runs those rows if there are any,
+    and returns ``(scores, idx)``.  Resolving a search one step late lets the host enqueue the next batch while the
+    GPU still scores this one (bench.py does that); ``search_shards(defer=False)`` resolves at once."""
+
+    def __init__(self, ctx):
+        self._ctx = ctx
+        self._done = ctx is None
+        self.scores = self.idx = None
+        self.reran = False                    # True once result() had to re-run rows (scores / idx were rewritten)
+
+    @classmethod
+    def ready(cls, scores, idx):
+        p = cls(None)
+        p.scores, p.idx = scores, idx
+        return p
+
+    def result(self):
+        if not self._done:
+            if self._ctx.dev.type == "cuda":
+                with torch.cuda.device(self._ctx.dev):
+                    self.reran = self._ctx.resolve()
+            else:
+                self.reran = self._ctx.resolve()
+            self._done = True
+            self._ctx = None
+        return self.scores, self.idx
+
+
+class _Search:
+    """State of one filtered search (every rank holds the same queries, thresholds and outputs)."""
+
+    def __init__(self, stores, comm, k, k_eff, kk, wts, excl, eps_t, pl, a_op, q_raw, q_norm, nq, thr, out_s, out_i,
+                 stats, ph):
+        self.stores, self.comm, self.k, self.k_eff, self.kk, self.wts = stores, comm, k, k_eff, kk, wts
+        self.excl, self.eps_t, self.pl = excl, eps_t, pl
+        self.a_op, self.q_raw, self.q_norm, self.nq, self.thr = a_op, q_raw, q_norm, nq, thr
+        self.out_s, self.out_i, self.stats, self.ph = out_s, out_i, stats, ph
+        self.ref = stores[0]
+        self.dev = self.ref.device
+        self.live = [s for s in stores if s.n]
+        self.n_shards = len(stores) * comm.world
+        self.solo = self.n_shards == 1
+        cap = pl["cap"]
+        if not self.solo:
+            cap = max(2048, min(cap, 1 << int(math.ceil(math.log2(4.0 * cap / self.n_shards)))))
+        self.cap = cap
+        self.n_shard_max = max(s.n for s in self.live) if self.live else 1
+        self.pending = None
+
+    # one pass over all rows (rows None) or over the rows that are re-run --------------------------------
+    def run_pass(self, rows):
+        ref, dev, comm, ph, k_eff, kk, eps_t = self.ref, self.dev, self.comm, self.ph, self.k_eff, self.kk, self.eps_t
+        if rows is None:
+            a_sub, q_sub, qn_sub, thr_sub, ex_sub, n_sub = self.a_op, self.q_raw, self.q_norm, self.thr, self.excl, self.nq
+        else:
+            n_sub = rows.numel()
+            a_sub = torch.zeros((_round_up(n_sub, _BM), ref.k), dtype=torch.bfloat16, device=dev)
+            a_sub[:n_sub] = self.a_op[rows]
+            q_sub = self.q_raw[rows].contiguous()
+            qn_sub = self.q_norm[:, rows].contiguous()
+            thr_sub = self.thr[rows].contiguous()
+            ex_sub = self.excl[rows].contiguous() if self.excl is not None else None
+        cap = self.cap
+        # 3: fused score + threshold filter on every local shard
+        ph.mark("alloc")
+        cands = [s._filter(a_sub, n_sub, thr_sub, cap) for s in self.live]
+        ph.mark("filter")
+        # 4: what needs an exact score
+        m = kk if self.solo else min(kk, int(math.ceil(1.5 * kk / self.n_shards)) + 10)
+        if kk <= PILOT_MAX:
+            # two rounds.  One: every shard rescores its m best approximate candidates; the k-th largest exact score
+            # of the union of these pilots (kth1) is a lower bound on the true k-th best.  Two: only candidates whose
+            # approximate score reaches kth1 - eps can still belong to the top-k.
+            firsts = [_row_kth(c[1], c[0], m, 0.0, 0) for c in cands]
+            exacts = [s._rescore(q_sub, qn_sub, n_sub, self.wts, c, b1) for s, c, b1 in zip(self.live, cands, firsts)]
+            pilots = [s._pilot_top(e, c, n_sub, ex_sub, m) for s, c, e in zip(self.live, cands, exacts)]
+            if not pilots:
+                pilots = [torch.full((n_sub, m), float("-inf"), dtype=torch.float64, device=dev)]
+            bound = _pilot_bound(_segments(pilots, comm), k_eff, eps_t)
+            ph.mark("pilot")
+            for s, c, b1, e in zip(self.live, cands, firsts, exacts):
+                s._rescore(q_sub, qn_sub, n_sub, self.wts, c, bound, b1, e)
+        else:
+            # very deep lists (k > 1000): one round against (kk-th largest approximate score over all shards) - 2 eps
+            if self.solo:
+                bound = _row_kth(cands[0][1], cands[0][0], kk, 2.0, 0, eps_t)
+            else:
+                tops = [_row_topj(c[1], c[0], kk) for c in cands]
+                if not tops:
+                    tops = [torch.full((n_sub, kk), float("-inf"), dtype=torch.float32, device=dev)]
+                bound = _row_kth(_union(tops, comm), None, kk, 2.0, 0, eps_t)
+            ph.mark("bound")
+            exacts = [s._rescore(q_sub, qn_sub, n_sub, self.wts, c, bound) for s, c in zip(self.live, cands)]
+        ph.mark("rescore")
+        # 5: selection.  One shard: the local kernel certifies.  Several: packed local lists, ONE gather, K3.
+        n_bad = torch.zeros((1,), dtype=torch.int32, device=dev)
+        if self.solo:
+            s_ = torch.empty((n_sub, k_eff), dtype=torch.float64, device=dev)
+            i_ = torch.empty((n_sub, k_eff), dtype=torch.int64, device=dev)
+            cert, thr_next = self.live[0]._select(exacts[0], cands[0], n_sub, k_eff, ex_sub, thr_sub, eps_t, bound,
+                                                  s_, i_, True, n_bad)
+            over = ("lists", [cands[0][0]], cap)
+        else:
+            seg = packed_bytes(n_sub, k_eff)
+            blocks = torch.empty((max(len(self.live), 1), seg), dtype=torch.uint8, device=dev)
+            for li, (s, c, e) in enumerate(zip(self.live, cands, exacts)):
+                b_s, b_i, b_f = packed_views(blocks[li], n_sub, k_eff)
+                s._select(e, c, n_sub, k_eff, ex_sub, None, eps_t, None, b_s, b_i, False)
+                b_f.copy_(c[0] > cap)
+            if not self.live:
+                b_s, b_i, b_f = packed_views(blocks[0], n_sub, k_eff)
+                b_s.fill_(float("-inf"))
+                b_i.fill_(-1)
+                b_f.zero_()
+            gathered = blocks if comm.world == 1 else comm.gather(blocks).view(-1, seg)
+            s_, i_, cert, thr_next = _merge_packed(gathered, n_sub, k_eff, k_eff, thr_sub, eps_t, n_bad)
+            over = ("packed", gathered, n_sub, k_eff)
+        ph.mark("select_merge")
+        if self.stats is not None and rows is None:
+            st = self.stats
+            st["eps"] = float(eps_t)
+            st["cap"] = cap
+            st["pilot_m"] = m
+            st["cand_count"] = [c[0] for c in cands]
+            st["rescored_per_query"] = sum(float((e[:, :cap] > float("-inf")).sum()) for e in exacts) / max(n_sub, 1) \
+                if all(torch.is_tensor(e) for e in exacts) else None
+            ph.mark("stats_bookkeeping")
+        return s_, i_, cert, thr_next, over, n_bad, thr_sub
+
+    def first_pass(self):
+        s_, i_, cert, thr_next, over, n_bad, thr_sub = self.run_pass(None)
+        self.out_s[:, :self.k_eff] = s_
+        self.out_i[:, :self.k_eff] = i_
+        self._last = (cert, thr_next, over, thr_sub)
+        if self.dev.type == "cuda":
+            self._flag = torch.empty((1,), dtype=torch.int32).pin_memory()
+            self._flag.copy_(n_bad, non_blocking=True)
+            self._event = torch.cuda.Event()
+            self._event.record()
+        else:
+            self._flag, self._event = n_bad, None
+
+    def resolve(self):
+        """Wait for the first pass's certificate count; re-run (all ranks alike) the rows that missed it."""
+        if self._event is not None:
+            self._event.synchronize()
+        self.ph.mark("certify_sync")
+        reran = int(self._flag[0]) != 0
+        if reran:
+            self._rerun()
+        if self.stats is not None:
+            self.stats["phases_ms"] = self.ph.result()
+        return reran
+
+    @staticmethod
+    def _overflowed(over):
+        """Per-row overflow flags of a pass (formed only when rows are re-run)."""
+        if over[0] == "lists":
+            return over[1][0] > over[2]
+        _, gathered, n_sub, k_eff = over
+        flags = torch.stack([packed_views(gathered[g], n_sub, k_eff)[2] for g in range(gathered.shape[0])])
+        return flags.max(dim=0).values != 0
+
+    def _rerun(self):
+        cert, thr_next, over, thr_sub = self._last
+        rows = None
+        for attempt in range(12):
+            bad = torch.nonzero(cert == 0).flatten()            # device -> host sync (identical on every rank)
+            if bad.numel() == 0:
+                return
+            over = self._overflowed(over)
+            # an overflowed row needs a HIGHER threshold; if the kernel cannot propose one, grow the lists
+            stuck = over[bad] & (thr_next[bad] <= thr_sub[bad])
+            if rows is None:
+                self.thr = self.thr.clone()
+                self.thr[bad] = thr_next[bad]
+                rows = bad
+            else:
+                self.thr[rows[bad]] = thr_next[bad]
+                rows = rows[bad]
+            if self.stats is not None:
+                self.stats["reruns"] = self.stats.get("reruns", 0) + 1
+                self.stats["rerun_rows"] = self.stats.get("rerun_rows", 0) + int(rows.numel())
+            if bool(stuck.any()):
+                # overflow that a tighter threshold cannot fix (dense neighbourhoods within eps of the k-th best):
+                # grow the lists -- for the few rows left they may grow until they hold a whole shard
+                room = max(32768, min(1 << int(math.ceil(math.log2(self.n_shard_max))),
+                                      (1 << 27) // max(int(rows.numel()), 1)))
+                self.cap = min(room, self.cap * 4)
+            s_, i_, cert, thr_next, over, _, thr_sub = self.run_pass(rows)
+            self.out_s[rows, :self.k_eff] = s_
+            self.out_i[rows, :self.k_eff] = i_
+        bad = torch.nonzero(cert == 0).flatten()
+        if bad.numel():
+            raise N.XmveError("search: %d row(s) could not be certified after 12 passes (increase eps headroom "
+                              "or candidate capacity; heavy score ties?)" % int(bad.numel()))
+
+
+def _dv2_global(stores, comm):
+    """max over ALL corpus rows (every shard of every rank) of the squared bf16 residual: device fp32 [1], cached per
+    corpus state -- the one all-reduce it needs is paid when the corpus changes, not per search."""
+    ref = stores[0]
+    key = (tuple(s.n for s in stores), comm.world)
+    cached = getattr(ref, "_dv2_cache", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    v = torch.stack([s.resid_max2().reshape(()) for s in stores]).max().reshape(1).float()
+    v = comm.max_(v)
+    ref._dv2_cache = (key, v)
+    return v
+
+
 def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, small_nv=SMALL_NV, stats=None, comm=None,
-                  n_total=None):
+                  n_total=None, defer=False):
     """Exact top-``k`` over a corpus cut into shards: ``stores`` are this process's shards (normally one), ``comm``
     joins the processes of a ``torch.distributed`` group (``distributed.GroupComm``; every rank calls this function
     with the same queries).  All shards work against ONE per-query threshold:
 
-    1. K1 on the query batch; the measured error bound ``eps`` (max over ranks).
+    1. K1 on the query batch; the measured error bound ``eps`` as a device scalar (the corpus-side maximum is
+       all-reduced once per corpus state, the query side is identical on every rank).
     2. the largest scores of a ``step``-strided sample of each shard (a coarse K2 STORE pass sets a floor, a K2
        FILTER pass over the sample keeps what exceeds it); the top-J of every shard are gathered and the global
        threshold is ``max(kth(union, j) - 2 eps, kth(union, j_cap))`` -- what one GPU would compute on the whole
        corpus, so each shard appends only its share of the candidates.
     3. K2 FILTER over each shard (the score matrix never reaches HBM).
-    4. the kk-th largest approximate candidate score over all shards - 2 eps bounds what needs an exact score.
-    5. exact fp64 rescore + local top-k per shard; ONE gather of the ``[nq, k]`` lists; merge (K3) with the
-       certificate ``kth_exact - eps >= threshold`` and no overflowed list.
-    6. rows without a certificate are re-run (by all ranks alike) with the threshold the merge proposes.
+    4. exact fp64 rescore in two rounds: every shard rescores its best ``m`` approximate candidates; the pilots are
+       gathered and the k-th largest exact score of their union, minus eps, bounds what the second round rescores
+       (about half of what the one-round window ``approximate k-th - 2 eps`` needs).
+    5. local top-k per shard into a packed block; ONE gather of the blocks; merge (K3) with the certificate
+       ``kth_exact - eps >= threshold`` and no overflowed list.
+    6. rows without a certificate are re-run (by all ranks alike) with the threshold the merge proposes.  Their
+       number is the only thing the host reads back, asynchronously: with ``defer=True`` the function returns a
+       :class:`PendingSearch` right after enqueueing steps 1-5 and ``.result()`` does step 6.
 
     Corpora of at most ``small_nv`` rows skip 2-4: every shard forms its fp64 score matrix directly.
     With one shard and one rank no gather happens and the certificate comes from the local selection kernel.
     """
     comm = comm or SoloComm()
+    ref = stores[0]
+    if ref.device.type == "cuda":
+        with torch.cuda.device(ref.device):                     # kernels, streams and allocations follow the store
+            pending = _search_shards(stores, queries, k, weights, exclude, eps, small_nv, stats, comm, n_total)
+            return pending if defer else pending.result()
+    pending = _search_shards(stores, queries, k, weights, exclude, eps, small_nv, stats, comm, n_total)
+    return pending if defer else pending.result()
+
+
+def _search_shards(stores, queries, k, weights, exclude, eps, small_nv, stats, comm, n_total):
     ref = stores[0]
     dev, n_space = ref.device, len(ref.dims)
     n_shards = len(stores) * comm.world
@@ -388,7 +713,8 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
     a_op, q_raw, q_norm, q_res, nq = ref.prepare_queries(queries, wts)
     ph.mark("prepare_queries")
     if nq == 0:
-        return (torch.empty((0, k), dtype=torch.float64, device=dev), torch.empty((0, k), dtype=torch.int64, device=dev))
+        return PendingSearch.ready(torch.empty((0, k), dtype=torch.float64, device=dev),
+                                   torch.empty((0, k), dtype=torch.int64, device=dev))
     excl = None
     if exclude is not None:
         excl = torch.as_tensor(exclude, dtype=torch.int64).to(dev)
@@ -407,21 +733,20 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
             s_, i_ = _merge(_union([p[0] for p in parts], comm), _union([p[1] for p in parts], comm), k_eff)
         out_s[:, :k_eff] = s_
         out_i[:, :k_eff] = i_
-        return out_s, out_i
+        return PendingSearch.ready(out_s, out_i)
 
+    w_abs = max(1.0, sum(abs(w) for w in wts))
     if eps is None:
-        m = torch.stack([q_res.sum(0).max(), torch.stack([s.resid_max2() for s in stores]).max()]).double()
-        dq2, dv2 = comm.max_(m).tolist()                       # host sync (tiny); the bound must be a host float
-        eps = measured_eps(math.sqrt(dq2), math.sqrt(dv2), wts, n_space, ref.k) if dq2 == dq2 and dv2 == dv2 \
-            else EPS_X1 * max(1.0, sum(abs(w) for w in wts))
+        eps_t = _eps_device(q_res, _dv2_global(stores, comm), wts, n_space, ref.k)
     else:
-        eps = float(eps) * max(1.0, sum(abs(w) for w in wts))
-    ph.mark("eps_sync")
+        eps_t = torch.full((1,), float(eps) * w_abs, dtype=torch.float32, device=dev)
+    ph.mark("eps")
     kk = k_eff + (1 if excl is not None else 0)               # one extra in case the excluded row is among them
     pl = plan(kk, n_total)
     live = [s for s in stores if s.n]
     # 2: one global threshold from the shards' samples
-    big_j = max(pl["j"], pl["j_cap"])
+    j_cap = pl["j_cap"] if solo else min(pl["j_cap"], ROW_TOPJ_MAX)      # xmve_row_topj holds 4096 values per row
+    big_j = max(pl["j"], j_cap)
     lists, floor = [], torch.full((nq,), float("-inf"), dtype=torch.float32, device=dev)
     for s in live:
         if (s.n + pl["step"] - 1) // pl["step"] >= 16384:
@@ -433,105 +758,28 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
             lists.append((s._sample(a_op, nq, pl["step"]), None))
             floor = torch.full_like(floor, float("-inf"))     # a complete list needs no floor
     if solo:
-        thr = _row_kth(lists[0][0], lists[0][1], pl["j"], 2.0 * eps, pl["j_cap"])
+        thr = _row_kth(lists[0][0], lists[0][1], pl["j"], 2.0, j_cap, eps_t)
     else:
         tops = [_row_topj(sc, cnt, big_j) for sc, cnt in lists]
         if not tops:
             tops = [torch.full((nq, big_j), float("-inf"), dtype=torch.float32, device=dev)]
-        thr = _row_kth(_union(tops, comm), None, pl["j"], 2.0 * eps, pl["j_cap"])
-        floor = -comm.max_(-floor)                            # min over the ranks
+        tops.append(floor.unsqueeze(1))                       # the floors ride along with the order statistics
+        u = _union(tops, comm)                                # [nq, G * (L * big_j + 1)]
+        per = u.shape[1] // comm.world
+        floor = u.view(nq, comm.world, per)[:, :, -1].min(dim=1).values
+        u.view(nq, comm.world, per)[:, :, -1] = float("-inf")
+        thr = _row_kth(u, None, pl["j"], 2.0, j_cap, eps_t)
     # a two-level list that came out too short gives -inf (or a value below the floor): fall back to the coarse
     # floor, which ~0.4 % of the corpus exceeds -- far more than k rows, so it is below the k-th best score
-    thr = torch.maximum(thr, floor - 2.0 * eps)
+    thr = torch.maximum(thr, floor - 2.0 * eps_t)
     del lists
     ph.mark("sample_threshold")
-    cap = pl["cap"] if solo else max(2048, min(pl["cap"], 1 << int(math.ceil(math.log2(4.0 * pl["cap"] / n_shards)))))
-    n_shard_max = max(s.n for s in live) if live else 1
-    rows = None                                               # None = all rows; else LongTensor of rows to re-run
-    for attempt in range(12):
-        if rows is None:
-            a_sub, q_sub, qn_sub, thr_sub, ex_sub, n_sub = a_op, q_raw, q_norm, thr, excl, nq
-        else:
-            n_sub = rows.numel()
-            a_sub = torch.zeros((_round_up(n_sub, _BM), ref.k), dtype=torch.bfloat16, device=dev)
-            a_sub[:n_sub] = a_op[rows]
-            q_sub = q_raw[rows].contiguous()
-            qn_sub = q_norm[:, rows].contiguous()
-            thr_sub = thr[rows].contiguous()
-            ex_sub = excl[rows].contiguous() if excl is not None else None
-        # 3: fused score + threshold filter on every local shard
-        ph.mark("alloc")
-        cands = [s._filter(a_sub, n_sub, thr_sub, cap) for s in live]
-        ph.mark("filter")
-        # 4: nothing below (kk-th largest approximate candidate score) - 2 eps can reach the top-k
-        if solo:
-            bound = _row_kth(cands[0][1], cands[0][0], kk, 2.0 * eps, 0)
-        else:
-            tops = [_row_topj(c[1], c[0], kk) for c in cands]
-            if not tops:
-                tops = [torch.full((n_sub, kk), float("-inf"), dtype=torch.float32, device=dev)]
-            bound = _row_kth(_union(tops, comm), None, kk, 2.0 * eps, 0)
-        ph.mark("bound")
-        # 5: exact rescore + selection
-        if solo:
-            s_, i_, cert, thr_next = live[0]._rescore_select(q_sub, qn_sub, n_sub, k_eff, wts, ex_sub, cands[0], bound,
-                                                             thr_sub, eps, True)
-            over = cands[0][0] > cap
-        else:
-            parts = [s._rescore_select(q_sub, qn_sub, n_sub, k_eff, wts, ex_sub, c, bound, thr_sub, eps, False)
-                     for s, c in zip(live, cands)]
-            over = torch.zeros((n_sub,), dtype=torch.int32, device=dev)
-            for c in cands:
-                over |= (c[0] > cap).int()
-            over = comm.max_(over)
-            if not parts:
-                parts = [(torch.full((n_sub, k_eff), float("-inf"), dtype=torch.float64, device=dev),
-                          torch.full((n_sub, k_eff), -1, dtype=torch.int64, device=dev), None, None)]
-            s_, i_, cert, thr_next = _merge(_union([p[0] for p in parts], comm), _union([p[1] for p in parts], comm),
-                                            k_eff, thr=thr_sub, eps=eps, overflow=over)
-            over = over != 0
-        ph.mark("rescore_select_merge")
-        if stats is not None and rows is None:
-            stats["eps"] = eps
-            stats["cap"] = cap
-            stats["cand_count"] = [c[0] for c in cands]
-            ar = torch.arange(cap, device=dev)
-            stats["rescored_per_query"] = sum(
-                float(((ar[None, :] < c[0][:, None]) & (c[1] >= bound[:, None])).sum()) for c in cands) / n_sub
-            ph.mark("stats_bookkeeping")
-        bad = torch.nonzero(cert == 0).flatten()              # device -> host sync (identical on every rank)
-        ph.mark("certify_sync")
-        if rows is None:
-            out_s[:, :k_eff] = s_
-            out_i[:, :k_eff] = i_
-        else:
-            out_s[rows, :k_eff] = s_
-            out_i[rows, :k_eff] = i_
-        if bad.numel() == 0:
-            break
-        # an overflowed row needs a HIGHER threshold; if the kernel cannot propose one, grow the lists
-        stuck = over[bad] & (thr_next[bad] <= thr_sub[bad])
-        if rows is None:
-            thr = thr.clone()
-            thr[bad] = thr_next[bad]
-            rows = bad
-        else:
-            thr[rows[bad]] = thr_next[bad]
-            rows = rows[bad]
-        if stats is not None:
-            stats["reruns"] = stats.get("reruns", 0) + 1
-            stats["rerun_rows"] = stats.get("rerun_rows", 0) + int(rows.numel())
-        if bool(stuck.any()):
-            # overflow that a tighter threshold cannot fix (dense neighbourhoods within eps of the k-th best): grow
-            # the lists -- for the few rows left they may grow until they hold a whole shard (cannot overflow then)
-            room = max(32768, min(1 << int(math.ceil(math.log2(n_shard_max))), (1 << 27) // max(int(rows.numel()), 1)))
-            cap = min(room, cap * 4)
-    else:
-        raise N.XmveError("search: %d row(s) could not be certified after 12 passes (increase eps headroom "
-                          "or candidate capacity; heavy score ties?)" % int(rows.numel()))
-    if stats is not None:
-        stats["phases_ms"] = ph.result()
-    return out_s, out_i
+    search = _Search(stores, comm, k, k_eff, kk, wts, excl, eps_t, pl, a_op, q_raw, q_norm, nq, thr, out_s, out_i,
+                     stats, ph)
+    search.first_pass()
+    pending = PendingSearch(search)
+    pending.scores, pending.idx = out_s, out_i
+    return pending
 
 
 def search_norm_score(stores, queries, k, weights=None, comm=None, n_total=None, **kw):
@@ -551,12 +799,17 @@ def search_norm_score(stores, queries, k, weights=None, comm=None, n_total=None,
     q_dev = [_to_device(x, ref.device) for x in _as_spaces(queries, ref.dims)]
     q_all = q_dev[0] if n_space == 1 else torch.cat(q_dev, dim=-1)
     adj, shift = [], 0.0
+    kw_ext = {key: v for key, v in kw.items() if key not in ("exclude", "stats", "defer")}   # extremes: all rows count
+    kw.pop("defer", None)
     for s in range(n_space):
         onehot = [1.0 if t == s else 0.0 for t in range(n_space)]
-        top, _ = search_shards(stores, q_all, 1, weights=onehot, comm=comm, n_total=n_total, **kw)
-        bot, _ = search_shards(stores, -q_all, 1, weights=onehot, comm=comm, n_total=n_total, **kw)
+        top, _ = search_shards(stores, q_all, 1, weights=onehot, comm=comm, n_total=n_total, **kw_ext)
+        bot, _ = search_shards(stores, -q_all, 1, weights=onehot, comm=comm, n_total=n_total, **kw_ext)
         hi, lo = float(top.max()), -float(bot.max())            # global extremes of cos_s over all (q, v)
         rng = hi - lo                                            # s / np.max(s) after s -= np.min(s)
+        if not rng > 0.0:
+            raise ValueError("search_norm_score: space %d has a constant score matrix (max == min); norm_score "
+                             "divides by zero there, as the reference's would (validate.py:10)" % s)
         adj.append(wts[s] / rng)
         shift += wts[s] * lo / rng
     scores, idx = search_shards(stores, q_all, k, weights=adj, comm=comm, n_total=n_total, **kw)
@@ -573,8 +826,8 @@ def _merge(scores, idx, k, thr=None, eps=0.0, overflow=None):
         cert = torch.empty((nq,), dtype=torch.int32, device=scores.device)
         thr_next = torch.empty((nq,), dtype=torch.float32, device=scores.device)
     if nq:
-        N.call("xmve_select_topk_i64", N.ptr(scores), N.ptr(idx), nq, m, None, k, N.ptr(thr), float(eps),
-               N.ptr(overflow), N.ptr(out_s), N.ptr(out_i), None, N.ptr(cert), N.ptr(thr_next), N.stream_ptr())
+        N.call("xmve_select_topk_i64", N.ptr(scores), N.ptr(idx), nq, m, None, k, N.ptr(thr), float(eps), None,
+               N.ptr(overflow), N.ptr(out_s), N.ptr(out_i), None, N.ptr(cert), N.ptr(thr_next), None, N.stream_ptr())
     if thr is None:
         return out_s, out_i
     return out_s, out_i, cert, thr_next

@@ -113,13 +113,17 @@ XMVE_API int xmve_score_filter(const void* a_op, int64_t nq, int64_t a_ld,
  * out[r] = max( kth_largest(row r, j1) - sub , kth_largest(row r, j2) )   (j2 <= 0: first term only)
  * Row r holds min(counts[r], cols) valid floats (counts == NULL: cols).  Fewer than j valid values
  * give -inf for that term.  Used for the sampled filter threshold and the candidate pre-filter.
+ * sub_dev (DEVICE scalar, may be NULL) multiplies sub: with the error bound eps living on the device (xmve_eps_bound)
+ * "kth - 2 eps" is sub = 2, sub_dev = eps -- no host round trip, the step stays capturable in a CUDA graph.
  */
 XMVE_API int xmve_row_kth(const float* vals, int64_t rows, int64_t cols, int64_t ld, const int32_t* counts,
-                 int32_t j1, float sub, int32_t j2, float* out, void* stream);
+                 int32_t j1, float sub, const float* sub_dev, int32_t j2, float* out, void* stream);
 
 /* ---- exact rescoring of candidates in double precision -----------------------------------------
  * exact[q, c] = sum_s w[s] * <q_s, v_s> / (||q_s|| * ||v_s||)  for candidate c of row q whose
- * approximate score is >= bound[q] (bound == NULL: all), else -inf.  Raw rows are fp32 (values the
+ * approximate score is >= bound[q] (bound == NULL: all), else -inf.  With bound_hi != NULL (the second round of the
+ * two-round rescore) only candidates with bound[q] <= approx < bound_hi[q] are computed and the entries at or above
+ * bound_hi[q] -- written by the first round -- are left untouched.  Raw rows are fp32 (values the
  * reference keeps in float64 arrays, evaluation.py:102-105); products and sums are in fp64, i.e.
  * the arithmetic of cal_error on float64 inputs (evaluation.py:19-21) up to rounding order.
  * space_off[n_space+1] (HOST array) are column offsets into the raw rows, weights[n_space] is a HOST
@@ -130,7 +134,30 @@ XMVE_API int xmve_rescore(const float* q_raw, int64_t nq, int64_t q_ld, const do
                  const float* v_raw, int64_t nv, int64_t v_ld, const double* v_norm,
                  int n_space, const int32_t* space_off, const double* weights, int norm_mode,
                  const float* cand_score, const int32_t* cand_idx, const int32_t* cand_count,
-                 int32_t cap, const float* bound, double* exact, void* stream);
+                 int32_t cap, const float* bound, const float* bound_hi, double* exact, void* stream);
+
+/* ---- two-round rescore: the pilot -----------------------------------------------------------------------
+ * Round one rescores the m best approximate candidates of every shard exactly.  xmve_pilot_top writes the (up to) m
+ * largest finite entries of exact[r, :min(counts[r], cap)] in descending order, -inf padded, skipping the entry whose
+ * global index idx + idx_offset equals exclude[r]: out fp64 [rows, m] (m <= 1024).  After the lists of all shards are
+ * gathered ([n_seg, rows, m]), xmve_pilot_bound gives bound[r] = round_down(kth largest of the union - eps) (-inf if
+ * the union has fewer than k finite scores): a candidate whose approximate score is below it cannot belong to the
+ * top-k, because the k-th largest of ANY set of exact scores is a lower bound on the true k-th best and
+ * |approx - exact| <= eps.  eps_dev as sub_dev above.  (Halves the rows gathered by the rescore against the one-round
+ * window "approximate k-th - 2 eps".)
+ */
+XMVE_API int xmve_pilot_top(const double* exact, const int32_t* idx, const int32_t* counts, int64_t rows, int32_t cap,
+                   int64_t idx_offset, const int64_t* exclude, int32_t m, double* out, void* stream);
+XMVE_API int xmve_pilot_bound(const double* lists, int32_t n_seg, int64_t rows, int32_t m, int32_t k, float eps,
+                     const float* eps_dev, float* bound, void* stream);
+
+/* The rigorous bound eps on |tensor-core score - exact score| from the MEASURED bf16 residuals, on the device:
+ * dq^2 = max_q sum_s q_resid[s, q], dv^2 = dv2[0] (max over corpus rows, all shards),
+ * eps = dq*vn + qn*dv + k_len * 2^-22 * qn * vn + 1e-6, qn = w_norm + dq, vn = sqrt(n_space) * (1 + 2^-8), rounded up;
+ * `fallback` when a residual is NaN (zero rows under XMVE_NORM_PLAIN).  eps_out: DEVICE float[1].
+ */
+XMVE_API int xmve_eps_bound(const float* q_resid, int32_t n_space, int64_t nq, const float* dv2, double w_norm,
+                   int32_t k_len, float fallback, float* eps_out, void* stream);
 
 /* ---- final top-k of each row from (score, index) pairs -----------------------------------------
  * Sorts the valid entries (score > -inf, index != exclude[r]) of row r by (score desc, index asc)
@@ -143,21 +170,35 @@ XMVE_API int xmve_rescore(const float* q_raw, int64_t nq, int64_t q_ld, const do
  * with (kth - eps when k entries were found; bound[r] = approximate kth of the retained candidates
  * - 2 eps after a candidate-list overflow).  The sort holds 16384 entries per row; rows with more valid entries
  * are first cut at the k-th largest score rounded to float (a superset of the exact top-k), so only > 16384
- * scores that agree with the k-th to float precision defeat it (reported as not certified).
+ * scores that agree with the k-th to float precision defeat it (reported as not certified).  (With 512 rows or more
+ * the sort holds max(2048, 4k) entries so that several rows are resident per SM; the rare row that does not fit comes
+ * back uncertified and is re-run in a small batch with the full capacity.)
+ * eps_dev (DEVICE scalar, may be NULL) multiplies eps.  n_uncertified (DEVICE int32, may be NULL) is incremented once
+ * per uncertified row: the caller reads ONE scalar, asynchronously, instead of scanning cert on the host.
  */
 XMVE_API int xmve_select_topk_i32(const double* score, const int32_t* idx, int64_t rows, int64_t cols,
                          const int32_t* counts, int64_t idx_offset, const int64_t* exclude, int32_t k,
-                         const float* thr, float eps, const float* bound,
+                         const float* thr, float eps, const float* eps_dev, const float* bound,
                          double* out_score, int64_t* out_idx, int32_t* out_valid,
-                         int32_t* cert, float* thr_next, void* stream);
+                         int32_t* cert, float* thr_next, int32_t* n_uncertified, void* stream);
 /* K3: G-way merge of per-shard top-k lists after the all-gather: rows x (G*k) pairs with global
  * int64 indices -> top-k.  Same ordering rule.  With thr != NULL the merged list is certified like above
  * (cert, thr_next); overflow[r] != 0 says that some shard's candidate list of row r overflowed. */
 XMVE_API int xmve_select_topk_i64(const double* score, const int64_t* idx, int64_t rows, int64_t cols,
                          const int64_t* exclude, int32_t k,
-                         const float* thr, float eps, const int32_t* overflow,
+                         const float* thr, float eps, const float* eps_dev, const int32_t* overflow,
                          double* out_score, int64_t* out_idx, int32_t* out_valid,
-                         int32_t* cert, float* thr_next, void* stream);
+                         int32_t* cert, float* thr_next, int32_t* n_uncertified, void* stream);
+/* K3 on the result of ONE all-gather: every rank contributes one packed block of seg_bytes bytes
+ *   [ score fp64 rows x len | global index int64 rows x len | overflow flag int32 rows | pad to 16 ]
+ * (xmve_packed_topk_bytes(rows, len) bytes), `packed` holds the n_seg blocks back to back.  Same ordering rule,
+ * certificate and outputs as xmve_select_topk_i64; a row is treated as overflowed if any block flags it.
+ */
+XMVE_API int64_t xmve_packed_topk_bytes(int64_t rows, int32_t len);
+XMVE_API int xmve_merge_topk_packed(const void* packed, int32_t n_seg, int64_t seg_bytes, int64_t rows, int32_t len,
+                           const int64_t* exclude, int32_t k, const float* thr, float eps, const float* eps_dev,
+                           double* out_score, int64_t* out_idx, int32_t* cert, float* thr_next,
+                           int32_t* n_uncertified, void* stream);
 /* The j largest values of each row in descending order, -inf padded: out fp32 [rows, j] (j <= 4096).
  * Row r holds min(counts[r], cols) valid values (counts == NULL: cols).  The j-th largest value of a corpus
  * that is sharded over GPUs is the j-th largest of the union of the shards' top-j lists. */

@@ -2,9 +2,10 @@
 
 ``engine.search_shards`` orchestrates kernels through a handful of shard-local methods and three module helpers.
 ``ModelShard`` restates those methods in torch-CPU arithmetic (bf16-rounded operands and fp32 scores for the
-filter, fp64 for the rescore) and :func:`patch_engine` swaps the three helpers, so that the control flow of the
-multi-rank pipeline -- the global threshold, the gathered rescore bound, the certified merge and the re-run loop in
-lockstep -- runs under the ``gloo`` backend without a GPU.  The kernels themselves are tested on the B200.
+filter, fp64 for the rescore) and :func:`patch_engine` swaps the module helpers, so that the control flow of the
+multi-rank pipeline -- the device-side error bound, the global threshold, the two-round rescore with its gathered
+pilot, the packed gather + certified merge and the re-run loop in lockstep -- runs under the ``gloo`` backend
+without a GPU.  The kernels themselves are tested on the B200.
 """
 import math
 
@@ -123,26 +124,59 @@ class ModelShard:
         count, score, _ = self._filter(a_op, nq, thr0, cap_s, step=step)
         return score, count, thr0
 
-    def _rescore_select(self, q_raw, q_norm, nq, k, wts, excl, cand, bound, thr, eps, certify):
+    def _rescore(self, q_raw, q_norm, nq, wts, cand, bound, bound_hi=None, exact=None):
         count, c_s, c_i = cand
         cap = c_s.shape[1]
         exact_all = self._exact(q_raw[:nq], q_norm[:, :nq], wts)
-        out_s, out_i, cert, nxt = [], [], [], []
+        if exact is None:
+            exact = torch.full((nq, cap), float("nan"), dtype=torch.float64)
+        ninf = torch.tensor(float("-inf"), dtype=torch.float64)
         for r in range(nq):
             n = min(int(count[r]), cap)
             idx = c_i[r, :n].long()
-            sc = torch.where(c_s[r, :n] >= bound[r], exact_all[r, idx], torch.tensor(float("-inf"), dtype=torch.float64))
-            s, i, n_valid = _sorted_topk(sc, idx, k, None if excl is None else int(excl[r]), self.index_offset)
-            out_s.append(s)
-            out_i.append(i)
+            approx = c_s[r, :n]
+            hi = float("inf") if bound_hi is None else float(bound_hi[r])
+            lo = float("-inf") if bound is None else float(bound[r])
+            mine = (approx >= lo) & (approx < hi)
+            row = exact[r, :n]
+            row[mine] = exact_all[r, idx[mine]]
+            row[approx < lo] = ninf
+        return exact
+
+    def _pilot_top(self, exact, cand, nq, excl, m):
+        count, c_s, c_i = cand
+        cap = c_s.shape[1]
+        out = torch.full((nq, m), float("-inf"), dtype=torch.float64)
+        for r in range(nq):
+            n = min(int(count[r]), cap)
+            sc = exact[r, :n]
+            keep = sc > float("-inf")
+            if excl is not None and int(excl[r]) >= 0:
+                keep &= (c_i[r, :n].long() + self.index_offset) != int(excl[r])
+            top = torch.sort(sc[keep], descending=True).values[:m]
+            out[r, : len(top)] = top
+        return out
+
+    def _select(self, exact, cand, nq, k, excl, thr, eps_t, bound, out_s, out_i, certify, n_bad=None):
+        count, c_s, c_i = cand
+        cap = c_s.shape[1]
+        eps = float(eps_t)
+        cert, nxt = [], []
+        for r in range(nq):
+            n = min(int(count[r]), cap)
+            s, i, n_valid = _sorted_topk(exact[r, :n], c_i[r, :n].long(), k, None if excl is None else int(excl[r]),
+                                         self.index_offset)
+            out_s[r], out_i[r] = s, i
             if certify:
                 c, x = _certify(float(s[k - 1]) if n_valid >= k else float("-inf"), n_valid, k, float(thr[r]), eps,
                                 int(count[r]) > cap, float(bound[r]))
                 cert.append(c)
                 nxt.append(x)
         if certify:
-            return torch.stack(out_s), torch.stack(out_i), torch.tensor(cert, dtype=torch.int32), torch.tensor(nxt)
-        return torch.stack(out_s), torch.stack(out_i), None, None
+            cert = torch.tensor(cert, dtype=torch.int32)
+            n_bad += int((cert == 0).sum())
+            return cert, torch.tensor(nxt)
+        return None, None
 
 
 def patch_engine(monkeypatch_setattr):
@@ -152,7 +186,9 @@ def patch_engine(monkeypatch_setattr):
     def kth(row, j):
         return float(torch.sort(row, descending=True).values[j - 1]) if 0 < j <= len(row) else float("-inf")
 
-    def row_kth(vals, counts, j1, sub, j2):
+    def row_kth(vals, counts, j1, sub, j2, sub_dev=None):
+        if sub_dev is not None:
+            sub = sub * float(sub_dev)
         out = []
         for r in range(vals.shape[0]):
             n = vals.shape[1] if counts is None else min(int(counts[r]), vals.shape[1])
@@ -184,6 +220,36 @@ def patch_engine(monkeypatch_setattr):
             nxt.append(x)
         return out_s, out_i, torch.tensor(cert, dtype=torch.int32), torch.tensor(nxt)
 
+    def eps_device(q_res, dv2, wts, n_space, k_len):
+        dq2 = float(q_res.sum(0).max())
+        return torch.tensor([engine.measured_eps(math.sqrt(dq2), math.sqrt(float(dv2)), wts, n_space, k_len)],
+                            dtype=torch.float32)
+
+    def pilot_bound(lists, k, eps_t):
+        n_seg, nq, m = lists.shape
+        out = []
+        for r in range(nq):
+            row = torch.sort(lists[:, r, :].reshape(-1), descending=True).values
+            kth = float(row[k - 1]) if k <= len(row) else float("-inf")
+            b = torch.tensor(kth - float(eps_t), dtype=torch.float64)
+            f = b.float()
+            if f.double() > b:                                   # round DOWN to float
+                f = torch.nextafter(f, torch.tensor(float("-inf")))
+            out.append(float(f) if kth > float("-inf") else float("-inf"))
+        return torch.tensor(out, dtype=torch.float32)
+
+    def merge_packed(packed, rows, length, k, thr, eps_t, n_bad):
+        views = [engine.packed_views(packed[g], rows, length) for g in range(packed.shape[0])]
+        scores = torch.cat([v[0] for v in views], dim=1)
+        idx = torch.cat([v[1] for v in views], dim=1)
+        over = torch.stack([v[2] for v in views]).max(dim=0).values
+        out_s, out_i, cert, nxt = merge(scores, idx, k, thr=thr, eps=float(eps_t), overflow=over)
+        n_bad += int((cert == 0).sum())
+        return out_s, out_i, cert, nxt
+
     monkeypatch_setattr(engine, "_row_kth", row_kth)
     monkeypatch_setattr(engine, "_row_topj", row_topj)
     monkeypatch_setattr(engine, "_merge", merge)
+    monkeypatch_setattr(engine, "_eps_device", eps_device)
+    monkeypatch_setattr(engine, "_pilot_bound", pilot_bound)
+    monkeypatch_setattr(engine, "_merge_packed", merge_packed)

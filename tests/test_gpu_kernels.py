@@ -192,7 +192,12 @@ def test_row_kth(N, rows, cols):
     counts = torch.randint(1, cols + 1, (rows,), generator=g, device="cuda", dtype=torch.int32)
     out = torch.empty(rows, device="cuda")
     j1, j2 = 3, 17
-    N.call("xmve_row_kth", N.ptr(x), rows, cols, cols, N.ptr(counts), j1, 0.5, j2, N.ptr(out), N.stream_ptr())
+    out_dev = torch.empty(rows, device="cuda")
+    half = torch.tensor([0.25], device="cuda")              # sub = 2 * sub_dev[0]: the device-side "2 eps"
+    N.call("xmve_row_kth", N.ptr(x), rows, cols, cols, N.ptr(counts), j1, 0.5, None, j2, N.ptr(out), N.stream_ptr())
+    N.call("xmve_row_kth", N.ptr(x), rows, cols, cols, N.ptr(counts), j1, 2.0, N.ptr(half), j2, N.ptr(out_dev),
+           N.stream_ptr())
+    assert torch.equal(out, out_dev)
     for r in range(rows):
         n = int(counts[r])
         srt = torch.sort(x[r, :n], descending=True).values
@@ -232,8 +237,12 @@ def test_select_topk_and_merge(N):
     thr = torch.full((rows,), -1.0, device="cuda")
     cert = torch.empty(rows, dtype=torch.int32, device="cuda")
     nxt = torch.empty(rows, device="cuda")
+    ten = torch.tensor([0.001], device="cuda")              # eps = 10 * eps_dev[0]
+    n_bad = torch.zeros(1, dtype=torch.int32, device="cuda")
     N.call("xmve_select_topk_i32", N.ptr(score), N.ptr(idx), rows, cols, N.ptr(counts), 1000, N.ptr(excl), k, N.ptr(thr),
-           0.01, None, N.ptr(out_s), N.ptr(out_i), N.ptr(valid), N.ptr(cert), N.ptr(nxt), N.stream_ptr())
+           10.0, N.ptr(ten), None, N.ptr(out_s), N.ptr(out_i), N.ptr(valid), N.ptr(cert), N.ptr(nxt), N.ptr(n_bad),
+           N.stream_ptr())
+    assert int(n_bad) == 0
     for r in range(rows):
         s = score[r, :cols - 5].clone()
         i = idx[r, :cols - 5].long() + 1000
@@ -256,6 +265,23 @@ def test_select_topk_and_merge(N):
     assert torch.equal(m_s, out_s) and torch.equal(m_i, out_i)
     r_s, r_i = distributed.merge_reference(sh_s, sh_i, k)
     assert torch.equal(r_s, out_s) and torch.equal(r_i, out_i)
+    # the same merge on PACKED per-rank blocks (what ONE all-gather delivers): [scores | rows | overflow flags]
+    seg = engine.packed_bytes(rows, k)
+    packed = torch.zeros((4, seg), dtype=torch.uint8, device="cuda")
+    for gi in range(4):
+        b_s, b_i, b_f = engine.packed_views(packed[gi], rows, k)
+        b_s.copy_(sh_s[gi])
+        b_i.copy_(sh_i[gi])
+    engine.packed_views(packed[2], rows, k)[2][5] = 1       # shard 2 reports an overflowed list for row 5
+    thr2 = torch.full((rows,), -1.0, device="cuda")
+    thr2[7] = 10.0                                          # a threshold row 7's k-th score cannot clear
+    n_bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    p_s, p_i, p_cert, p_nxt = engine._merge_packed(packed, rows, k, k, thr2, ten, n_bad)
+    assert torch.equal(p_s, out_s) and torch.equal(p_i, out_i)
+    want_cert = torch.ones(rows, dtype=torch.int32, device="cuda")
+    want_cert[5] = 0
+    want_cert[7] = 0
+    assert torch.equal(p_cert, want_cert) and int(n_bad) == 2
 
 
 def test_select_topk_more_valid_entries_than_the_sort_holds(N):
@@ -274,9 +300,10 @@ def test_select_topk_more_valid_entries_than_the_sort_holds(N):
     thr = torch.full((rows,), -10.0, device="cuda")
     cert = torch.empty(rows, dtype=torch.int32, device="cuda")
     nxt = torch.empty(rows, device="cuda")
+    n_bad = torch.zeros(1, dtype=torch.int32, device="cuda")
     N.call("xmve_select_topk_i32", N.ptr(score), N.ptr(idx), rows, cols, N.ptr(counts), 0, None, k, N.ptr(thr), 1e-3,
-           None, N.ptr(out_s), N.ptr(out_i), N.ptr(valid), N.ptr(cert), N.ptr(nxt), N.stream_ptr())
-    assert (valid == cols).all()
+           None, None, N.ptr(out_s), N.ptr(out_i), N.ptr(valid), N.ptr(cert), N.ptr(nxt), N.ptr(n_bad), N.stream_ptr())
+    assert (valid == cols).all() and int(n_bad) == 1
     for r in range(rows):
         if r == 1:                       # 40 000 scores that agree to float precision: reported as not certified
             assert int(cert[r]) == 0
@@ -305,7 +332,21 @@ def test_rescore_is_fp64_exact(N):
     off = (C.c_int32 * 3)(0, 100, 128)
     w = (C.c_double * 2)(0.7, 0.3)
     N.call("xmve_rescore", N.ptr(q), nq, 128, N.ptr(qn), N.ptr(v), nv, 128, N.ptr(vn), 2, off, w, 0, N.ptr(approx),
-           N.ptr(idx), N.ptr(count), cap, N.ptr(bound), N.ptr(exact), N.stream_ptr())
+           N.ptr(idx), N.ptr(count), cap, N.ptr(bound), None, N.ptr(exact), N.stream_ptr())
+    # two rounds give the same array: [0.5, inf) first, then [-0.3, 0.5) with the first round left untouched
+    hi = torch.full((nq,), 0.5, device="cuda")
+    lo = torch.full((nq,), -0.3, device="cuda")
+    two = torch.full((nq, cap), 123.0, dtype=torch.float64, device="cuda")
+    N.call("xmve_rescore", N.ptr(q), nq, 128, N.ptr(qn), N.ptr(v), nv, 128, N.ptr(vn), 2, off, w, 0, N.ptr(approx),
+           N.ptr(idx), N.ptr(count), cap, N.ptr(hi), None, N.ptr(two), N.stream_ptr())
+    first = two.clone()
+    N.call("xmve_rescore", N.ptr(q), nq, 128, N.ptr(qn), N.ptr(v), nv, 128, N.ptr(vn), 2, off, w, 0, N.ptr(approx),
+           N.ptr(idx), N.ptr(count), cap, N.ptr(lo), N.ptr(hi), N.ptr(two), N.stream_ptr())
+    one = torch.full((nq, cap), 123.0, dtype=torch.float64, device="cuda")
+    N.call("xmve_rescore", N.ptr(q), nq, 128, N.ptr(qn), N.ptr(v), nv, 128, N.ptr(vn), 2, off, w, 0, N.ptr(approx),
+           N.ptr(idx), N.ptr(count), cap, N.ptr(lo), None, N.ptr(one), N.stream_ptr())
+    assert torch.equal(two, one)
+    assert torch.equal(two[approx >= 0.5], first[approx >= 0.5])
     for r in range(nq):
         n = min(int(count[r]), cap)
         rows = v[idx[r, :n].long()].double()
@@ -390,9 +431,9 @@ def test_list_ranks(N):
     np.cumsum(sizes, out=off[1:])
     flat = np.concatenate(wanted).astype(np.int64)
     rank = torch.empty(len(flat), dtype=torch.int32, device="cuda")
-    l_d = torch.from_numpy(lists).cuda()
-    N.call("xmve_list_ranks", N.ptr(l_d), nq, kk, kk, N.ptr(torch.from_numpy(off).cuda()),
-           N.ptr(torch.from_numpy(flat).cuda()), len(flat), n_mem + 1, N.ptr(rank), N.stream_ptr())
+    l_d, off_d, flat_d = torch.from_numpy(lists).cuda(), torch.from_numpy(off).cuda(), torch.from_numpy(flat).cuda()
+    N.call("xmve_list_ranks", N.ptr(l_d), nq, kk, kk, N.ptr(off_d), N.ptr(flat_d), len(flat), n_mem + 1, N.ptr(rank),
+           N.stream_ptr())
     want = []
     for q in range(nq):
         pos = {int(v): p + 1 for p, v in reversed(list(enumerate(lists[q]))) if v >= 0}
@@ -414,3 +455,76 @@ def test_ap_at_k_with_a_huge_relevant_set(N):
         ranks = [pos.get(int(r), n_shots + 1) for r in relevant[q]]
         assert ap[q] == _ap_reference(ranks, n_shots, 1000)
     assert m == np.mean(ap)
+
+
+# ---- two-round rescore: pilot kernels, device-side eps -------------------------------------------------------
+def test_pilot_top_and_bound(N):
+    from cross_modal_video_engine_b200 import engine
+    g = torch.Generator(device="cuda").manual_seed(31)
+    rows, cap, m, k, n_seg = 50, 700, 40, 100, 4
+    lists = []
+    for seg in range(n_seg):
+        exact = torch.randn((rows, cap), generator=g, device="cuda", dtype=torch.float64)
+        exact[torch.rand((rows, cap), generator=g, device="cuda") < 0.8] = float("-inf")     # not rescored
+        exact[1] = float("-inf")                                                             # a row with no pilot at all
+        idx = torch.stack([torch.randperm(5000, generator=g, device="cuda")[:cap] for _ in range(rows)]).int()
+        counts = torch.randint(cap // 2, cap + 100, (rows,), generator=g, device="cuda", dtype=torch.int32)
+        excl = idx[:, 3].long() + 7 * seg                                                    # an entry of every row
+        out = torch.empty((rows, m), dtype=torch.float64, device="cuda")
+        N.call("xmve_pilot_top", N.ptr(exact), N.ptr(idx), N.ptr(counts), rows, cap, 7 * seg, N.ptr(excl), m, N.ptr(out),
+               N.stream_ptr())
+        for r in range(rows):
+            n = min(int(counts[r]), cap)
+            keep = (exact[r, :n] > float("-inf")) & (idx[r, :n].long() + 7 * seg != excl[r])
+            ref = torch.sort(exact[r, :n][keep], descending=True).values[:m]
+            assert torch.equal(out[r, : len(ref)], ref) and torch.all(out[r, len(ref):] == float("-inf"))
+        lists.append(out)
+    union = torch.stack(lists)                                                               # [n_seg, rows, m]
+    eps = torch.tensor([0.004], device="cuda")
+    for kk in (1, 37, 100, 161):
+        bound = engine._pilot_bound(union, kk, eps)
+        for r in range(rows):
+            allv = torch.sort(union[:, r, :].reshape(-1), descending=True).values
+            if kk <= len(allv) and allv[kk - 1] > float("-inf"):
+                want = allv[kk - 1].item() - float(eps)
+                got = bound[r].item()
+                assert got <= want and want - got < 1e-6 * max(1.0, abs(want))               # rounded DOWN to float
+            else:
+                assert bound[r].item() == float("-inf")
+
+
+def test_eps_bound_matches_the_host_formula(N):
+    import math
+    from cross_modal_video_engine_b200 import engine
+    g = torch.Generator(device="cuda").manual_seed(32)
+    q_res = torch.rand((2, 5000), generator=g, device="cuda") * 3e-6
+    dv2 = torch.tensor([2.9e-6], device="cuda")
+    wts = [0.6, 0.4]
+    got = float(engine._eps_device(q_res, dv2, wts, 2, 2048))
+    want = engine.measured_eps(math.sqrt(float(q_res.sum(0).max())), math.sqrt(float(dv2)), wts, 2, 2048)
+    assert want <= got <= want * (1 + 1e-6)                                                   # rounded UP to float
+    q_res[1, 17] = float("nan")                                                               # a zero row: a-priori bound
+    assert float(engine._eps_device(q_res, dv2, wts, 2, 2048)) == pytest.approx(engine.EPS_X1, rel=1e-6)
+
+
+def test_select_topk_many_rows_use_the_small_sort(N):
+    """>= 512 rows: the sort holds max(2048, 4k) entries; a row with more valid scores is cut at its k-th largest
+    rounded score first and must still come out right and certified."""
+    rows, cols, k = 600, 6000, 100
+    g = torch.Generator(device="cuda").manual_seed(33)
+    score = torch.randn((rows, cols), generator=g, device="cuda", dtype=torch.float64)
+    score[:, 300:] = float("-inf")
+    score[5] = torch.randn(cols, generator=g, device="cuda", dtype=torch.float64)             # 6000 valid entries
+    idx = torch.stack([torch.randperm(cols, generator=g, device="cuda") for _ in range(rows)]).int()
+    counts = torch.full((rows,), cols, dtype=torch.int32, device="cuda")
+    out_s = torch.empty((rows, k), dtype=torch.float64, device="cuda")
+    out_i = torch.empty((rows, k), dtype=torch.int64, device="cuda")
+    thr = torch.full((rows,), -10.0, device="cuda")
+    cert = torch.empty(rows, dtype=torch.int32, device="cuda")
+    nxt = torch.empty(rows, device="cuda")
+    n_bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    N.call("xmve_select_topk_i32", N.ptr(score), N.ptr(idx), rows, cols, N.ptr(counts), 0, None, k, N.ptr(thr), 1e-3,
+           None, None, N.ptr(out_s), N.ptr(out_i), None, N.ptr(cert), N.ptr(nxt), N.ptr(n_bad), N.stream_ptr())
+    assert int(n_bad) == 0 and bool((cert == 1).all())
+    top_s, top_p = torch.topk(score, k, dim=1)
+    assert torch.equal(out_s, top_s) and torch.equal(out_i, torch.gather(idx.long(), 1, top_p))

@@ -4,7 +4,10 @@ C1 is covered by the golden fixture ``c1_1k`` (tests/test_gpu_parity.py).  C2 ru
 in well under a minute).  C3-C5 are too large for the CPU oracle, so they are checked through size-independent
 properties and against a plain torch fp64 statement of the same scores computed on the device in chunks (a
 library matmul used ONLY as the checker): identical top-k index lists, scores within 1e-12, planted items found,
-AP@1000 identical to the oracle's scorer on the exact ranks.
+AP@1000 identical to the oracle's scorer on the exact ranks.  The checker never reads what the product wrote
+(``store.raw`` / ``store.norm``): it REGENERATES every corpus chunk from the seed, re-applies the planted rows,
+pools the frames and takes the norms itself -- a row-placement or norm bug of K1 (e.g. beyond 2^31 bytes) would
+show up as a mismatch.
 """
 import time
 
@@ -31,44 +34,18 @@ def X():
     return ns
 
 
-def _fp64_topk(raw, norm, q_raw, dims, weights, k, chunk=1 << 18, exclude=None):
-    """Exact top-k of sum_s w_s * cos_s in torch fp64 on the device, corpus walked in chunks.
-    ``raw`` fp32 [nv, sum(dims)], ``norm`` fp64 [S, nv] (the store's buffers), ``q_raw`` fp32 [nq, sum(dims)]."""
-    nq = q_raw.shape[0]
-    offs = np.cumsum((0,) + tuple(dims))
-    qn = []
-    for s, (a, b) in enumerate(zip(offs[:-1], offs[1:])):
-        q = q_raw[:, a:b].double()
-        qn.append(weights[s] * q / torch.linalg.vector_norm(q, dim=1, keepdim=True))
-    best_s = torch.full((nq, 0), 0.0, dtype=torch.float64, device=raw.device)
-    best_i = torch.full((nq, 0), 0, dtype=torch.int64, device=raw.device)
-    for lo in range(0, raw.shape[0], chunk):
-        hi = min(raw.shape[0], lo + chunk)
-        sc = torch.zeros((nq, hi - lo), dtype=torch.float64, device=raw.device)
-        for s, (a, b) in enumerate(zip(offs[:-1], offs[1:])):
-            v = raw[lo:hi, a:b].double() / norm[s, lo:hi, None]
-            sc += qn[s] @ v.T
-        if exclude is not None:
-            hit = (exclude >= lo) & (exclude < hi)
-            sc[torch.nonzero(hit).flatten(), (exclude[hit] - lo)] = float("-inf")
-        ids = torch.arange(lo, hi, device=raw.device).expand(nq, -1)
-        cs, ci = torch.cat([best_s, sc], 1), torch.cat([best_i, ids], 1)
-        # (score desc, index asc): sort by index first (already ascending within and across chunks), stable by score
-        order = torch.argsort(cs, dim=1, descending=True, stable=True)[:, :k]
-        best_s, best_i = torch.gather(cs, 1, order), torch.gather(ci, 1, order)
-        order = torch.argsort(best_i, dim=1, stable=True)              # keep candidates index-ascending for stability
-        best_s, best_i = torch.gather(best_s, 1, order), torch.gather(best_i, 1, order)
-    order = torch.argsort(best_s, dim=1, descending=True, stable=True)
-    return torch.gather(best_s, 1, order), torch.gather(best_i, 1, order)
+def _dedupe_plant(rows, vecs):
+    """Keep the FIRST vector planted at each row (an index_put with duplicate rows is not deterministic)."""
+    pos = torch.arange(rows.numel(), device=rows.device)
+    uniq, inv = torch.unique(rows, return_inverse=True)
+    first = torch.full((uniq.numel(),), rows.numel(), dtype=torch.int64, device=rows.device)
+    first.scatter_reduce_(0, inv, pos, reduce="amin")
+    return uniq, vecs[first]
 
 
-def _device_store(X, nv, dims, seed, chunk=250000, plant=None, frames=1, norm_mode="plain"):
-    """Corpus generated on the device chunk by chunk; ``plant = (rows, vectors)`` overwrites some rows."""
-    import gc
-    gc.collect()
-    torch.cuda.empty_cache()                     # the stores of earlier tests are gone; hand their blocks back
-    store = X.engine.CorpusStore(nv, dims, norm_mode=norm_mode)
-    d = sum(dims)
+def _chunks(X, nv, d, seed, chunk=250000, plant=None, frames=1):
+    """The synthetic corpus chunk by chunk, generated on the device from the seed: yields ``(lo, rows)`` with
+    ``rows`` fp32 ``[n, d]`` or ``[n, frames, d]``; ``plant = (rows, vectors)`` overwrites some rows."""
     for c, lo in enumerate(range(0, nv, chunk)):
         n = min(chunk, nv - lo)
         buf = X.synth.device_gaussian(n * frames, d, seed * 100003 + c, "cuda")
@@ -82,6 +59,60 @@ def _device_store(X, nv, dims, seed, chunk=250000, plant=None, frames=1, norm_mo
                     buf[rows[m] - lo] = vecs[m].unsqueeze(1).expand(-1, frames, -1).contiguous()
                 else:
                     buf[rows[m] - lo] = vecs[m]
+        yield lo, buf
+
+
+def _fp64_topk(X, q_raw, nv, dims, weights, k, seed, chunk=250000, plant=None, frames=1, eps_norm=False,
+               exclude=None):
+    """Exact top-k of sum_s w_s * cos_s in torch fp64 on the device, from corpus rows REGENERATED from the seed
+    (independent of the store): frames pooled as fp32 ``(f0 + f1 + ...) / T`` (Combiner.time_process on fp32
+    features), norms in fp64 (``eps_norm``: ``max(norm, 1e-12)`` as F.normalize), order (score desc, row asc)."""
+    nq = q_raw.shape[0]
+    dev = q_raw.device
+    offs = np.cumsum((0,) + tuple(dims))
+    qn = []
+    for s, (a, b) in enumerate(zip(offs[:-1], offs[1:])):
+        q = q_raw[:, a:b].double()
+        nrm = torch.linalg.vector_norm(q, dim=1, keepdim=True)
+        qn.append(weights[s] * q / (nrm.clamp(min=1e-12) if eps_norm else nrm))
+    best_s = torch.full((nq, 0), 0.0, dtype=torch.float64, device=dev)
+    best_i = torch.full((nq, 0), 0, dtype=torch.int64, device=dev)
+    for lo, buf in _chunks(X, nv, sum(dims), seed, chunk, plant, frames):
+        if frames > 1:
+            acc = buf[:, 0].clone()
+            for f in range(1, frames):
+                acc += buf[:, f]
+            buf = acc / float(frames)
+        hi = lo + buf.shape[0]
+        sc = torch.zeros((nq, hi - lo), dtype=torch.float64, device=dev)
+        for s, (a, b) in enumerate(zip(offs[:-1], offs[1:])):
+            v = buf[:, a:b].double()
+            nrm = torch.linalg.vector_norm(v, dim=1, keepdim=True)
+            v /= nrm.clamp(min=1e-12) if eps_norm else nrm
+            sc += qn[s] @ v.T
+            del v
+        if exclude is not None:
+            hit = (exclude >= lo) & (exclude < hi)
+            sc[torch.nonzero(hit).flatten(), (exclude[hit] - lo)] = float("-inf")
+        ids = torch.arange(lo, hi, device=dev).expand(nq, -1)
+        cs, ci = torch.cat([best_s, sc], 1), torch.cat([best_i, ids], 1)
+        # (score desc, index asc): candidates are kept index-ascending, the sort by score is stable
+        order = torch.argsort(cs, dim=1, descending=True, stable=True)[:, :k]
+        best_s, best_i = torch.gather(cs, 1, order), torch.gather(ci, 1, order)
+        order = torch.argsort(best_i, dim=1, stable=True)
+        best_s, best_i = torch.gather(best_s, 1, order), torch.gather(best_i, 1, order)
+        del sc, cs, ci, buf
+    order = torch.argsort(best_s, dim=1, descending=True, stable=True)
+    return torch.gather(best_s, 1, order), torch.gather(best_i, 1, order)
+
+
+def _device_store(X, nv, dims, seed, chunk=250000, plant=None, frames=1, norm_mode="plain"):
+    """Corpus generated on the device chunk by chunk (:func:`_chunks`) and appended to a resident store."""
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()                     # the stores of earlier tests are gone; hand their blocks back
+    store = X.engine.CorpusStore(nv, dims, norm_mode=norm_mode)
+    for _, buf in _chunks(X, nv, sum(dims), seed, chunk, plant, frames):
         store.add(buf)
     return store
 
@@ -140,7 +171,7 @@ def test_c3_avs_shape_top1000_and_map(X):
     s, i = X.avs.search_avs(store, Q, k)
     torch.cuda.synchronize()
     t_search = time.time() - t0
-    ref_s, ref_i = _fp64_topk(store.raw[:nv], store.norm[:, :nv], Q, (d,), (1.0,), k)
+    ref_s, ref_i = _fp64_topk(X, Q, nv, (d,), (1.0,), k, 51, plant=(rows, vecs))
     assert torch.equal(i, ref_i)
     torch.testing.assert_close(s, ref_s, rtol=0, atol=1e-12)
     # relevant set: the 40 planted shots + 500 random ones per query; AP@1000 == the oracle's scorer on the ranks
@@ -165,8 +196,8 @@ def test_c4_multifusion_shape(X):
     P = torch.nn.functional.normalize(X.synth.device_gaussian(nq, d, 62, "cuda"), dim=-1)
     tvec = P * 1.2 + 0.15 * X.synth.device_gaussian(nq, d, 63, "cuda")      # near the query after mean-pooling
     rvec = P * 3.0                                                        # the reference item scores highest
-    store = _device_store(X, nv, (d,), 60, chunk=125000, frames=frames, norm_mode="eps",
-                          plant=(torch.cat([target, reference]), torch.cat([tvec, rvec])))
+    plant = _dedupe_plant(torch.cat([target, reference]), torch.cat([tvec, rvec]))   # targets win over references
+    store = _device_store(X, nv, (d,), 60, chunk=125000, frames=frames, norm_mode="eps", plant=plant)
     names = torch.randperm(10 * nv, device="cuda", generator=g)[:nv].cpu().numpy().astype(np.int64)
     t0 = time.time()
     metrics, top_names = X.multifusion.cirr_metrics_from_features(P, None, names, names[reference.cpu().numpy()],
@@ -174,8 +205,8 @@ def test_c4_multifusion_shape(X):
     torch.cuda.synchronize()
     t_all = time.time() - t0
     sub = slice(0, 256)                                                    # checker on a slice of the queries
-    ref_s, ref_i = _fp64_topk(store.raw[:nv], store.norm[:, :nv].clamp(min=1e-12), P[sub], (d,), (1.0,), 100,
-                              exclude=reference[sub])
+    ref_s, ref_i = _fp64_topk(X, P[sub], nv, (d,), (1.0,), 100, 60, chunk=125000, frames=frames, eps_norm=True,
+                              plant=plant, exclude=reference[sub])
     np.testing.assert_array_equal(top_names[sub], names[ref_i.cpu().numpy()])
     assert metrics[:3] == (-1, -1, -1)
     labels = torch.from_numpy(top_names[:, :50]) == torch.from_numpy(names[target.cpu().numpy()])[:, None]
@@ -204,7 +235,7 @@ def test_c5_scale_sweep_full_shape(X):
     assert torch.all(s[:, :-1] >= s[:, 1:]) and torch.all(i >= 0)
     assert torch.all((s[:, :-1] > s[:, 1:]) | (i[:, :-1] < i[:, 1:]))     # ties (if any) by ascending index
     sub = torch.arange(0, nq, 64, device="cuda")                          # 128 queries against the fp64 checker
-    ref_s, ref_i = _fp64_topk(store.raw[:nv], store.norm[:, :nv], Q[sub], dims, w, k)
+    ref_s, ref_i = _fp64_topk(X, Q[sub], nv, dims, w, k, 4, plant=(plant_rows, plant_vecs))
     assert torch.equal(i[sub], ref_i)
     torch.testing.assert_close(s[sub], ref_s, rtol=0, atol=1e-12)
     print("C5 8192 x 10M x 2048 top-100: %.1f ms, eps %.2e, %d rerun rows" % (t_search * 1e3, stats["eps"],

@@ -327,6 +327,99 @@ extern "C" int xmve_list_ranks(const int64_t* lists, int64_t n_query, int64_t le
   return launch_status("list_ranks_kernel");
 }
 
+namespace xmve {
+namespace {
+// Rank of a ground-truth item from a candidate list (corpora whose score matrix cannot exist): entry e owns the
+// exact scores of the candidates whose approximate score fell into the guard band around its ground truth's score.
+// before[e] += #{c : exact[e, c] > s_gt[e]  or  (exact[e, c] == s_gt[e] and global index of c < g[e])} -- the
+// candidates that precede the ground truth in a stable ascending argsort of the errors (util/metrics.py:139-145).
+// One warp per entry.
+__global__ void __launch_bounds__(256)
+count_before_kernel(const double* __restrict__ exact, const int32_t* __restrict__ idx,
+                    const int32_t* __restrict__ counts, int cap, int64_t idx_offset,
+                    const double* __restrict__ s_gt, const int64_t* __restrict__ g, int64_t n_entries,
+                    long long* __restrict__ before) {
+  const int64_t e = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (e >= n_entries) return;
+  const int n = min(counts[e], cap);
+  const double s = s_gt[e];
+  const int64_t gi = g[e];
+  int c = 0;
+  for (int i = lane; i < n; i += 32) {
+    const double x = exact[e * cap + i];
+    const int64_t id = static_cast<int64_t>(idx[e * cap + i]) + idx_offset;
+    c += (x > s || (x == s && id < gi)) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0 && c != 0) atomicAdd(reinterpret_cast<unsigned long long*>(&before[e]), static_cast<unsigned long long>(c));
+}
+
+// The same question against a chunk of an exact fp64 score matrix (the fallback for ground truths so deep that the
+// guard band of the tensor-core pass overflows): scores [n_entries, cols] cover global columns col0 .. col0+cols.
+// Values above s_gt + delta are counted; the few inside |x - s_gt| <= delta (delta ~ 1e-13: the two fp64 summation
+// orders agree to ~1e-15) are appended to a per-entry list and settled by the rescore kernel's own arithmetic.
+__global__ void __launch_bounds__(256)
+count_band_f64_kernel(const double* __restrict__ scores, int64_t cols, int64_t ld, int64_t col0,
+                      const double* __restrict__ s_gt, double delta, int64_t n_entries,
+                      long long* __restrict__ above, int32_t* __restrict__ band_count, int32_t* __restrict__ band_idx,
+                      int band_cap) {
+  const int64_t e = blockIdx.y;
+  const double s = s_gt[e];
+  const double* row = scores + e * ld;
+  int c = 0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < cols;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const double x = row[i];
+    if (x > s + delta) {
+      ++c;
+    } else if (x >= s - delta) {
+      const int slot = atomicAdd(&band_count[e], 1);
+      if (slot < band_cap) band_idx[e * band_cap + slot] = static_cast<int32_t>(i);   // column within the chunk
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c != 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(&above[e]), static_cast<unsigned long long>(c));
+}
+}  // namespace
+}  // namespace xmve
+
+extern "C" int xmve_count_before(const double* exact, const int32_t* idx, const int32_t* counts, int64_t n_entries,
+                                 int32_t cap, int64_t idx_offset, const double* s_gt, const int64_t* g,
+                                 int64_t* before, void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  XMVE_REQUIRE(exact && idx && counts && s_gt && g && before && n_entries >= 0 && cap > 0, "count_before: bad arguments");
+  if (n_entries == 0) return XMVE_OK;
+  const int64_t blocks = (n_entries + 7) / 8;
+  if (blocks > 2147483647LL) return fail(XMVE_ERR_LIMIT, "count_before: too many entries");
+  count_before_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      exact, idx, counts, cap, idx_offset, s_gt, g, n_entries, reinterpret_cast<long long*>(before));
+  return launch_status("count_before_kernel");
+}
+
+extern "C" int xmve_count_band_f64(const double* scores, int64_t n_entries, int64_t cols, int64_t ld, int64_t col0,
+                                   const double* s_gt, double delta, int64_t* above, int32_t* band_count,
+                                   int32_t* band_idx, int32_t band_cap, void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  XMVE_REQUIRE(scores && s_gt && above && band_count && band_idx && n_entries >= 0 && cols > 0 && ld >= cols &&
+                   band_cap > 0 && delta >= 0.0, "count_band_f64: bad arguments");
+  if (n_entries == 0) return XMVE_OK;
+  if (n_entries > 65535) return fail(XMVE_ERR_LIMIT, "count_band_f64: more than 65535 entries per call; chunk it");
+  (void)col0;
+  int bx = static_cast<int>((cols + 2047) / 2048);
+  if (bx > 64) bx = 64;
+  dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>(n_entries));
+  count_band_f64_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      scores, cols, ld, col0, s_gt, delta, n_entries, reinterpret_cast<long long*>(above), band_count, band_idx,
+      band_cap);
+  return launch_status("count_band_f64_kernel");
+}
+
 extern "C" int xmve_rank_metrics(const int32_t* ranks, const int64_t* gt_off, int64_t n_query, int64_t n_mem,
                                  int first_only, int ap_k, int32_t max_gt, int32_t* sort_scratch, int32_t* best,
                                  double* ap, int64_t* recall_counts, int64_t* rank_sum, int32_t* hist, void* stream) {

@@ -42,6 +42,10 @@ class GroupComm:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return t
 
+    def sum_(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
     def sum_int(self, v):
         dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
         t = torch.tensor([int(v)], dtype=torch.int64, device=dev)

@@ -246,6 +246,18 @@ class CorpusStore:
                N.stream_ptr())
         return cand_count, cand_score, cand_idx
 
+    def _filter_band(self, a_op, nq, lo, hi, cap):
+        """K2 FILTER with a two-sided window per row: rows scoring above ``hi`` are counted, rows in ``(lo, hi]``
+        are listed -> (above int32 [nq], count int32 [nq], scores fp32 [nq, cap], local rows int32 [nq, cap])."""
+        dev = self.device
+        above = torch.zeros((nq,), dtype=torch.int32, device=dev)
+        count = torch.zeros((nq,), dtype=torch.int32, device=dev)
+        c_s = torch.empty((nq, cap), dtype=torch.float32, device=dev)
+        c_i = torch.empty((nq, cap), dtype=torch.int32, device=dev)
+        N.call("xmve_score_filter", N.ptr(a_op), nq, a_op.stride(0), N.ptr(self.op), self.n, self.op.stride(0), 1,
+               self.k, N.ptr(lo), N.ptr(hi), N.ptr(above), N.ptr(count), N.ptr(c_s), N.ptr(c_i), cap, N.stream_ptr())
+        return above, count, c_s, c_i
+
     def _sample_top(self, a_op, nq, step, big_j):
         """The largest scores of the ``step``-strided sample of this shard WITHOUT writing the sample matrix:
         a coarse STORE pass (every ``r * step``-th row, a few thousand columns) gives a per-query floor ``thr0``
@@ -364,6 +376,9 @@ class SoloComm:
     def sum_int(self, v):
         return int(v)
 
+    def sum_(self, t):
+        return t
+
 
 def _row_topj(vals, counts, j):
     rows, cols = vals.shape
@@ -389,6 +404,15 @@ def _eps_device(q_res, dv2, wts, n_space, k_len):
     N.call("xmve_eps_bound", N.ptr(q_res), n_space, q_res.shape[1], N.ptr(dv2), math.sqrt(sum(w * w for w in wts)),
            int(k_len), EPS_X1 * max(1.0, sum(abs(w) for w in wts)), N.ptr(out), N.stream_ptr())
     return out
+
+
+def _count_before(exact, cand_idx, counts, idx_offset, s_gt, g, out):
+    """``out[e] += #{candidates of entry e that precede its ground truth}`` (exact score above ``s_gt[e]``, or equal
+    with a smaller global row than ``g[e]``)."""
+    n_ent, cap = exact.shape
+    if n_ent:
+        N.call("xmve_count_before", N.ptr(exact), N.ptr(cand_idx), N.ptr(counts), n_ent, cap, int(idx_offset),
+               N.ptr(s_gt), N.ptr(g), N.ptr(out), N.stream_ptr())
 
 
 def _pilot_bound(lists, k, eps_t):
@@ -780,6 +804,133 @@ def _search_shards(stores, queries, k, weights, exclude, eps, small_nv, stats, c
     pending = PendingSearch(search)
     pending.scores, pending.idx = out_s, out_i
     return pending
+
+
+def rank_of_gt(stores, queries, gt_off, gt_rows, weights=None, comm=None, n_total=None, cap=8192, eps=None,
+               stats=None):
+    """EXACT rank of every ground-truth item when the score matrix cannot exist (C3-C5 scale), sharded.
+
+    ``gt_off`` int64 ``[nq + 1]`` / ``gt_rows`` int64 ``[E]`` are a CSR of global corpus rows per query (host arrays
+    or tensors).  Returns ``ranks`` int32 ``[E]`` on the device: ``1 + #{v : s(v) > s(g)} + #{v < g : s(v) == s(g)}``
+    with ``s`` the exact fp64 fused score -- the position of ``g`` in the stable ascending argsort of the reference's
+    errors row (``util/metrics.py:139-145``).  Feed them to ``metrics.RankResult.from_ranks`` for R@K / MedR / MeanR /
+    mAP.
+
+    1. the shard that owns ``g`` computes ``s(g)`` with the rescore kernel; one all-reduce(max) shares it.
+    2. the tensor-core FILTER runs with one operand row per ENTRY and the window ``(s(g) - eps, s(g) + eps]``:
+       rows above the window are counted (they are certainly better: ``|approx - exact| <= eps``), rows inside it
+       are listed, rescored exactly and compared with ``s(g)`` (``xmve_count_before``); rows below are certainly
+       worse.  Shards add their counts with ONE all-reduce(sum).
+    3. entries whose window holds more than ``cap`` rows (ground truths ranked tens of thousands deep) fall back to
+       an exact fp64 pass over the corpus (chunked ``xmve_score_f64`` + ``xmve_count_band_f64``).
+    """
+    comm = comm or SoloComm()
+    stores = list(stores) if isinstance(stores, (list, tuple)) else [stores]
+    ref = stores[0]
+    dev, n_space = ref.device, len(ref.dims)
+    wts = _weights(weights, n_space)
+    if n_total is None:
+        n_total = comm.sum_int(sum(s.n for s in stores))
+    import contextlib
+    with (torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()):
+        a_op, q_raw, q_norm, q_res, nq = ref.prepare_queries(queries, wts)
+        off = torch.as_tensor(gt_off, dtype=torch.int64)
+        g = torch.as_tensor(gt_rows, dtype=torch.int64).to(dev)
+        n_ent = int(g.numel())
+        assert off.numel() == nq + 1 and int(off[-1]) == n_ent, "gt_off must be a CSR over the query rows"
+        if n_ent == 0:
+            return torch.zeros((0,), dtype=torch.int32, device=dev)
+        owner = torch.repeat_interleave(torch.arange(nq), off[1:] - off[:-1]).to(dev)        # entry -> query row
+        if eps is None:
+            eps_t = _eps_device(q_res, _dv2_global(stores, comm), wts, n_space, ref.k)
+        else:
+            eps_t = torch.full((1,), float(eps) * max(1.0, sum(abs(w) for w in wts)), dtype=torch.float32, device=dev)
+        # one operand / raw row per entry
+        a_ent = torch.zeros((_round_up(n_ent, _BM), ref.k), dtype=torch.bfloat16, device=dev)
+        a_ent[:n_ent] = a_op[owner]
+        q_ent = q_raw[owner].contiguous()
+        qn_ent = q_norm[:, owner].contiguous()
+        live = [s for s in stores if s.n]
+        # 1: exact score of every ground-truth item, from the shard that owns it
+        s_gt = torch.full((n_ent,), float("-inf"), dtype=torch.float64, device=dev)
+        for s in live:
+            mine = (g >= s.index_offset) & (g < s.index_offset + s.n)
+            loc = torch.where(mine, g - s.index_offset, torch.zeros_like(g)).to(torch.int32).unsqueeze(1).contiguous()
+            cnt = mine.to(torch.int32)
+            ex = s._rescore(q_ent, qn_ent, n_ent, wts, (cnt, torch.zeros((n_ent, 1), device=dev), loc), None)
+            s_gt = torch.where(mine, ex[:, 0], s_gt)
+        s_gt = comm.max_(s_gt)
+        if bool((s_gt == float("-inf")).any()):
+            raise IndexError("rank_of_gt: a ground-truth row is outside the corpus (or its score is not finite)")
+        # 2: window around s(g), widened by the float roundings of its ends
+        e64 = eps_t.double()
+        lo = (s_gt - 1.001 * e64 - 1e-7).float()
+        hi = (s_gt + 1.001 * e64 + 1e-7).float()
+        tally = torch.zeros((2, n_ent), dtype=torch.int64, device=dev)                        # [before, overflowed]
+        for s in live:
+            above, count, c_s, c_i = s._filter_band(a_ent, n_ent, lo, hi, cap)
+            ex = s._rescore(q_ent, qn_ent, n_ent, wts, (count, c_s, c_i), None)
+            tally[0] += above
+            _count_before(ex, c_i, count, s.index_offset, s_gt, g, tally[0])
+            tally[1] += (count > cap)
+            del ex, c_s, c_i
+        tally = comm.sum_(tally)
+        deep = torch.nonzero(tally[1] != 0).flatten()                                         # host sync
+        if stats is not None:
+            stats["eps"] = float(eps_t)
+            stats["deep_entries"] = int(deep.numel())
+        # 3: exact fp64 pass for the entries whose window overflowed
+        if deep.numel():
+            fix = _rank_deep(live, q_ent[deep].contiguous(), qn_ent[:, deep].contiguous(), s_gt[deep].contiguous(),
+                             g[deep].contiguous(), wts)
+            tally[0, deep] = comm.sum_(fix)
+        return (tally[0] + 1).to(torch.int32)
+
+
+def _rank_deep(live, q_ent, qn_ent, s_gt, g, wts, chunk=1 << 17, band_cap=64, delta=1e-13):
+    """#{rows before the ground truth} over this rank's shards from an exact fp64 score matrix, chunk by chunk.
+    Scores more than ``delta`` above ``s_gt`` are counted; the handful within ``delta`` (the fp64 matrix and the
+    rescore kernel sum in different orders, ~1e-15 apart) are settled by the rescore kernel itself."""
+    dev = q_ent.device
+    n_ent = q_ent.shape[0]
+    before = torch.zeros((n_ent,), dtype=torch.int64, device=dev)
+    st = N.stream_ptr()
+    for s in live:
+        for e0 in range(0, n_ent, 4096):
+            e1 = min(n_ent, e0 + 4096)
+            ne = e1 - e0
+            qs_n, o = [], 0
+            for d in s.dims:
+                qn = torch.empty((ne, d), dtype=torch.float64, device=dev)
+                src = q_ent[e0:e1, o:o + d]
+                N.call("xmve_normalize_f64", N.ptr(src), N.F32, ne, d, q_ent.stride(0), N.ptr(qn), d, s.norm_mode, st)
+                qs_n.append(qn)
+                o += d
+            for r0 in range(0, s.n, chunk):
+                r1 = min(s.n, r0 + chunk)
+                acc, o = None, 0
+                for si, d in enumerate(s.dims):
+                    vn = torch.empty((r1 - r0, d), dtype=torch.float64, device=dev)
+                    vs = s.raw[r0:r1, o:o + d]
+                    N.call("xmve_normalize_f64", N.ptr(vs), N.F32, r1 - r0, d, s.raw.stride(0), N.ptr(vn), d,
+                           s.norm_mode, st)
+                    sc = torch.empty((ne, r1 - r0), dtype=torch.float64, device=dev)
+                    N.call("xmve_score_f64", N.ptr(qs_n[si]), ne, d, N.ptr(vn), r1 - r0, d, d, float(wts[si]),
+                           N.ptr(sc), r1 - r0, st)
+                    acc = sc if acc is None else acc.add_(sc)
+                    o += d
+                bcount = torch.zeros((ne,), dtype=torch.int32, device=dev)
+                bidx = torch.zeros((ne, band_cap), dtype=torch.int32, device=dev)
+                N.call("xmve_count_band_f64", N.ptr(acc), ne, r1 - r0, r1 - r0, r0, N.ptr(s_gt[e0:]), float(delta),
+                       N.ptr(before[e0:]), N.ptr(bcount), N.ptr(bidx), band_cap, st)
+                if bool((bcount > band_cap).any()):
+                    raise N.XmveError("rank_of_gt: more than %d corpus rows tie with a ground truth to 1e-13" % band_cap)
+                bidx += r0                                                                    # shard-local rows
+                ex = s._rescore(q_ent[e0:e1], qn_ent[:, e0:e1].contiguous(), ne, wts,
+                                (bcount, torch.zeros((ne, band_cap), device=dev), bidx), None)
+                _count_before(ex, bidx, bcount, s.index_offset, s_gt[e0:e1], g[e0:e1], before[e0:e1])
+                del acc, ex
+    return before
 
 
 def search_norm_score(stores, queries, k, weights=None, comm=None, n_total=None, **kw):

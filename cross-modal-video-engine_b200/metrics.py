@@ -66,6 +66,15 @@ def rank_metrics(ranks, off, n_query, n_mem, first_only, ap_k, max_gt, best=None
            N.ptr(tallies[3:]) if tallies is not None else None, N.ptr(hist), N.stream_ptr())
 
 
+def _csr64(gts, n_query):
+    """:func:`_csr` with int64 ids (global corpus rows of a 10 M-row corpus still fit int32; shards' offsets may not)."""
+    counts = np.fromiter((len(gts[i]) for i in range(n_query)), dtype=np.int64, count=n_query)
+    off = np.zeros(n_query + 1, dtype=np.int64)
+    np.cumsum(counts, out=off[1:])
+    ids = np.fromiter((x for i in range(n_query) for x in gts[i]), dtype=np.int64, count=int(off[-1]))
+    return off, ids, int(counts.max()) if n_query else 0
+
+
 def _device_matrix(scores):
     N.require_device()
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -103,6 +112,36 @@ class RankResult:
         self._x = x
         self.max_gt = max_gt
         self.reduce(first_only, ap_k)
+
+    @classmethod
+    def from_store(cls, stores, queries, gts, weights=None, comm=None, n_total=None, first_only=False, ap_k=0,
+                   stats=None, **kw):
+        """The same ranks and reductions for a corpus whose score matrix cannot exist: the
+        queries are scored against the resident (possibly sharded) ``CorpusStore`` and ``engine.rank_of_gt`` returns
+        the EXACT rank of every ground-truth row -- position in the stable ascending argsort of the errors row the
+        reference would form (util/metrics.py:139-145).  ``gts[i]`` lists the ground-truth GLOBAL corpus rows of
+        query i (list of lists, or dict by row like ``t2v_gt``)."""
+        from . import engine
+        stores = list(stores) if isinstance(stores, (list, tuple)) else [stores]
+        self = cls.__new__(cls)
+        q = queries[0] if isinstance(queries, (list, tuple)) else queries
+        self.n_query = int(q.shape[0])
+        off, ids, self.max_gt = _csr64(gts, self.n_query)
+        if n_total is None:
+            comm_ = comm or engine.SoloComm()
+            n_total = comm_.sum_int(sum(s.n for s in stores))
+        self.n_mem = int(n_total)
+        if ids.size and (ids.min() < 0 or ids.max() >= self.n_mem):
+            raise IndexError("ground-truth id out of range")
+        dev = stores[0].device
+        self.off = torch.from_numpy(off).to(dev)
+        self.ids = torch.from_numpy(ids).to(dev)
+        ranks = engine.rank_of_gt(stores, queries, off, ids, weights=weights, comm=comm, n_total=n_total, stats=stats,
+                                  **kw)
+        self.ranks = ranks if ranks.numel() else torch.zeros(1, dtype=torch.int32, device=dev)
+        self._x = None
+        self.reduce(first_only, ap_k)
+        return self
 
     def reduce(self, first_only=False, ap_k=0):
         dev, st = self.ranks.device, N.stream_ptr()
@@ -154,7 +193,25 @@ def v2t_map(c2i, v2t_gts):
     return RankResult(c2i_t, v2t_gts).mean_ap()
 
 
-# ---- the same metrics from top-k lists (corpora whose score matrix cannot exist) -------------------------
+# ---- the same metrics, EXACT, against a resident (sharded) corpus whose score matrix cannot exist ----------------
+def eval_q2m_store(stores, queries, q2m_gts, **kw):
+    """``eval_q2m`` (util/metrics.py:124-157) without the matrix: exact ``(r1, r5, r10, medr, meanr)`` of the queries
+    against the resident corpus.  ``**kw``: ``weights``, ``comm`` (``distributed.GroupComm``), ``n_total``."""
+    return RankResult.from_store(stores, queries, q2m_gts, **kw).recall_medr_meanr()
+
+
+def t2v_map_store(stores, queries, t2v_gts, **kw):
+    """``t2v_map`` (util/metrics.py:61-79) without the matrix (only the FIRST ground truth counts, :72-73)."""
+    return RankResult.from_store(stores, queries, t2v_gts, first_only=True, **kw).mean_ap()
+
+
+def v2t_map_store(stores, queries, v2t_gts, **kw):
+    """``v2t_map`` (util/metrics.py:83-102) without the matrix: the queries are the videos, the resident corpus holds
+    the captions, every ground-truth caption is relevant."""
+    return RankResult.from_store(stores, queries, v2t_gts, **kw).mean_ap()
+
+
+# ---- the same metrics from top-k lists (approximate beyond the list: prefer the exact functions above) -----------
 def eval_q2m_topk(idx, q2m_gts, n_m):
     """``eval_q2m`` (util/metrics.py:124-157) from ranked top-k lists instead of the score matrix: ``idx`` int64
     ``[n_q, k]`` from ``CorpusStore.search`` / ``sharded_search``, ``q2m_gts[i]`` the ground-truth rows of query i,

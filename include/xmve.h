@@ -259,6 +259,23 @@ XMVE_API int xmve_rank_metrics(const int32_t* ranks, const int64_t* gt_off, int6
 XMVE_API int xmve_list_ranks(const int64_t* lists, int64_t n_query, int64_t len, int64_t ld, const int64_t* off,
                     const int64_t* wanted, int64_t n_entries, int32_t absent, int32_t* rank, void* stream);
 
+/* ---- rank of the ground truth when the score matrix cannot exist (util/metrics.py:139-145 at C3-C5 scale) ---------
+ * Entry e = (query, ground-truth item g[e]) with the item's exact score s_gt[e].  The tensor-core pass
+ * (xmve_score_filter with lo = s_gt - eps, hi = s_gt + eps) counts the rows certainly above and lists the rows inside
+ * the guard band; after xmve_rescore of those, xmve_count_before adds
+ *   before[e] += #{c < min(counts[e], cap) : exact[e, c] > s_gt[e]  or  (exact[e, c] == s_gt[e] and idx + idx_offset < g[e])}
+ * so that rank = 1 + count_above + before is the position of g in a stable ascending argsort of the errors.
+ * Shards add their counts (one all-reduce).  xmve_count_band_f64 is the fallback for entries whose band overflowed
+ * (very deep ground truths): against a chunk of an exact fp64 score matrix [n_entries, cols] it adds the columns above
+ * s_gt + delta to above[e] and lists the columns with |x - s_gt| <= delta (chunk-local numbers) for the same settle step.
+ */
+XMVE_API int xmve_count_before(const double* exact, const int32_t* idx, const int32_t* counts, int64_t n_entries,
+                      int32_t cap, int64_t idx_offset, const double* s_gt, const int64_t* g, int64_t* before,
+                      void* stream);
+XMVE_API int xmve_count_band_f64(const double* scores, int64_t n_entries, int64_t cols, int64_t ld, int64_t col0,
+                        const double* s_gt, double delta, int64_t* above, int32_t* band_count, int32_t* band_idx,
+                        int32_t band_cap, void* stream);
+
 /* ---- norm_score (LINAS-engine/validate.py:7-11) -------------------------------------------------
  * minmax[0] = min(-E), minmax[1] = max(-E - min) over the whole matrix (two launches inside);
  * xmve_norm_score_apply writes out = -((-E - min) / max) with the reference's operation order.

@@ -113,6 +113,20 @@ class ModelShard:
             c_s[r, :m], c_i[r, :m] = sc[r, hit[:m]], hit[:m].int()
         return count, c_s, c_i
 
+    def _filter_band(self, a_op, nq, lo, hi, cap):
+        sc = (a_op[:nq].float() @ self.op.T).float()
+        above = (sc > hi[:, None]).sum(1).int()
+        count = torch.zeros(nq, dtype=torch.int32)
+        c_s = torch.full((nq, cap), float("nan"), dtype=torch.float32)
+        c_i = torch.zeros((nq, cap), dtype=torch.int32)
+        for r in range(nq):
+            hit = torch.nonzero((sc[r] > lo[r]) & (sc[r] <= hi[r])).flatten()
+            hit = hit[torch.randperm(len(hit), generator=torch.Generator().manual_seed(r))]
+            count[r] = len(hit)
+            m = min(len(hit), cap)
+            c_s[r, :m], c_i[r, :m] = sc[r, hit[:m]], hit[:m].int()
+        return above, count, c_s, c_i
+
     def _sample_top(self, a_op, nq, step, big_j):
         from cross_modal_video_engine_b200 import engine
         n_s = (self.n + step - 1) // step
@@ -247,6 +261,13 @@ def patch_engine(monkeypatch_setattr):
         n_bad += int((cert == 0).sum())
         return out_s, out_i, cert, nxt
 
+    def count_before(exact, cand_idx, counts, idx_offset, s_gt, g, out):
+        for e in range(exact.shape[0]):
+            n = min(int(counts[e]), exact.shape[1])
+            x, ids = exact[e, :n], cand_idx[e, :n].long() + idx_offset
+            out[e] += int(((x > s_gt[e]) | ((x == s_gt[e]) & (ids < g[e]))).sum())
+
+    monkeypatch_setattr(engine, "_count_before", count_before)
     monkeypatch_setattr(engine, "_row_kth", row_kth)
     monkeypatch_setattr(engine, "_row_topj", row_topj)
     monkeypatch_setattr(engine, "_merge", merge)

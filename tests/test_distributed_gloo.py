@@ -94,6 +94,20 @@ def _pipeline_worker(rank, world, port, out_dir):
     s2, i2 = engine.search_shards([shard], Q, 5, comm=distributed.GroupComm(), n_total=nv, small_nv=10 ** 9)
     ref2 = [cpu_model._sorted_topk(exact[r], torch.arange(nv), 5) for r in range(nq)]
     ok = ok and all(torch.equal(i2[r], ref2[r][1]) for r in range(nq))
+    # exact rank of ground-truth rows without the matrix (engine.rank_of_gt): owner-shard scores shared by
+    # all-reduce(max), per-shard guard-band counts added by all-reduce(sum) -- vs ranks from the full exact matrix
+    gts = [[int(grid[qi, 0])] + ([int(grid[qi, 3]), int((qi * 977) % nv)] if qi % 2 else []) for qi in range(nq)]
+    off = [0]
+    for gq in gts:
+        off.append(off[-1] + len(gq))
+    flat = [x for gq in gts for x in gq]
+    ranks = engine.rank_of_gt([shard], Q, off, flat, comm=distributed.GroupComm(), n_total=nv)
+    want = []
+    for qi, gq in enumerate(gts):
+        for gid in gq:
+            row = exact[qi]
+            want.append(1 + int((row > row[gid]).sum()) + int(((row == row[gid]) & (torch.arange(nv) < gid)).sum()))
+    ok = ok and ranks.tolist() == want and max(want) > 100       # planted (rank ~1) and arbitrary (deep) items
     with open(os.path.join(out_dir, "prank%d" % rank), "w") as f:
         f.write("ok" if ok else "mismatch")
     dist.destroy_process_group()

@@ -407,3 +407,65 @@ def test_planted_neighbours_found_at_1m(X):
     s2, i2 = store2.search(Q, k)
     assert torch.equal(perm[i2], i)
     torch.testing.assert_close(s2, s, rtol=0, atol=1e-14)
+
+
+# ---- exact ground-truth ranks without the score matrix (engine.rank_of_gt) -------------------
+def _planted_eval_set(X, nv=200_000, nq=600, d=128, sigma=4.5, seed=15):
+    V, Q, vid, cap, _ = X.synth.msrvtt_like(seed, nv, 1, d, sigma)
+    return V, Q[:nq], vid, cap[:nq]
+
+
+def test_rank_metrics_against_a_resident_corpus_equal_the_reference(X):
+    """eval_q2m / t2v_map of the reference on the FULL error matrix (oracle) == the same metrics computed against
+    the resident store without ever forming the matrix: exact ranks from the tensor-core pass with a guard band."""
+    V, Q, vid, cap = _planted_eval_set(X)
+    store = X.engine.CorpusStore(len(V), (128,)).add(torch.from_numpy(V))
+    _, t2v_gt = linas.get_gt(vid, cap)
+    err = linas.cal_error(V.astype(np.float64), Q.astype(np.float64))
+    ref = linas.eval_q2m(err, t2v_gt)
+    stats = {}
+    res = X.metrics.RankResult.from_store(store, torch.from_numpy(Q), t2v_gt, first_only=True, stats=stats)
+    np.testing.assert_array_equal(res.ranks.cpu().numpy(), linas.gt_ranks(err, t2v_gt))       # every rank, exactly
+    assert res.recall_medr_meanr() == ref and 5.0 < ref[0] < 95.0
+    assert res.mean_ap() == linas.t2v_map(err, t2v_gt)
+    assert X.metrics.eval_q2m_store(store, torch.from_numpy(Q), t2v_gt) == ref
+    assert X.metrics.t2v_map_store(store, torch.from_numpy(Q), t2v_gt) == linas.t2v_map(err, t2v_gt)
+    assert stats["deep_entries"] == 0
+
+
+def test_rank_of_gt_deep_fallback_and_multi_gt(X):
+    """A tiny candidate capacity forces the exact fp64 fallback for the deep ground truths; several ground truths
+    per query (the v2t direction: AP over all of them) -- all ranks == the oracle's."""
+    V, Q, vid, cap = _planted_eval_set(X, nv=60_000, nq=40, d=96, sigma=3.0, seed=16)
+    rng = np.random.default_rng(3)
+    gts = [[int(cap[i].split("#")[0][5:])] + rng.integers(0, len(V), 4).tolist() for i in range(len(Q))]
+    store = X.engine.CorpusStore(len(V), (96,)).add(torch.from_numpy(V))
+    err = linas.cal_error(V.astype(np.float64), Q.astype(np.float64))
+    off = np.cumsum([0] + [len(g) for g in gts])
+    flat = [x for g in gts for x in g]
+    want = []
+    for qi, gq in enumerate(gts):
+        order = np.argsort(err[qi], kind="stable")
+        pos = np.empty(len(V), np.int64)
+        pos[order] = np.arange(len(V))
+        want += [int(pos[x]) + 1 for x in gq]
+    for cap_, deep in ((8192, False), (16, True)):
+        stats = {}
+        ranks = X.engine.rank_of_gt([store], torch.from_numpy(Q), off, flat, cap=cap_, stats=stats)
+        assert ranks.cpu().tolist() == want
+        assert (stats["deep_entries"] > 0) == deep
+    res = X.metrics.RankResult.from_store(store, torch.from_numpy(Q), gts)
+    assert res.mean_ap() == np.mean([linas.ap_from_ranks(want[off[i]:off[i + 1]], nr_relevant=5, k=0, list_len=len(V))
+                                     for i in range(len(Q))])
+
+
+def test_rank_of_gt_over_two_shards_and_two_spaces(X):
+    dims, w = (96, 32), (0.7, 0.3)
+    V, Q, vid, cap = _planted_eval_set(X, nv=150_000, nq=300, d=sum(dims), sigma=5.0, seed=17)
+    cut = 80_001
+    shards = [X.engine.CorpusStore(cut, dims).add(torch.from_numpy(V[:cut])),
+              X.engine.CorpusStore(len(V) - cut, dims, index_offset=cut).add(torch.from_numpy(V[cut:]))]
+    _, t2v_gt = linas.get_gt(vid, cap)
+    V64, Q64 = V.astype(np.float64), Q.astype(np.float64)
+    err = linas.fused_errors([V64[:, :96], V64[:, 96:]], [Q64[:, :96], Q64[:, 96:]], w)
+    assert X.metrics.eval_q2m_store(shards, torch.from_numpy(Q), t2v_gt, weights=w) == linas.eval_q2m(err, t2v_gt)

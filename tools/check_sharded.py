@@ -4,7 +4,8 @@
 
 Every rank holds one shard of a seeded corpus; ``distributed.sharded_search`` over NCCL must return, on every rank,
 exactly what ONE store holding the whole corpus returns (indices identical, fp64 scores identical), with and
-without exclusions, for the filtered path and the small-corpus path, plus ``upload_rows`` and the AVS AP.
+without exclusions, for the filtered path and the small-corpus path, plus ``upload_rows``, the AVS AP and the exact
+ground-truth ranks of ``engine.rank_of_gt``.
 """
 import os
 import sys
@@ -14,7 +15,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from cross_modal_video_engine_b200 import avs, distributed, engine, synth  # noqa: E402
+from cross_modal_video_engine_b200 import avs, distributed, engine, metrics, synth  # noqa: E402
 
 
 def main():
@@ -39,6 +40,20 @@ def main():
             if rank == 0:
                 print("nv=%d nq=%d k=%d exclude=%s: %s" % (nv, nq, k, ex is not None, "identical" if same else "MISMATCH"),
                       flush=True)
+        if k == 100:
+            # exact ground-truth ranks without the matrix: owner-shard scores (all-reduce max) + per-shard guard-band
+            # counts (all-reduce sum) == the same on one store; R@K / MedR / MeanR / mAP identical
+            gts = [[int(x) for x in torch.randint(0, nv, (1 + q % 3,), generator=torch.Generator().manual_seed(q))]
+                   for q in range(nq)]
+            comm = distributed.GroupComm()
+            a = metrics.RankResult.from_store(shard, Q, gts, weights=w, comm=comm, n_total=nv)
+            b = metrics.RankResult.from_store(full, Q, gts, weights=w)
+            same = bool(torch.equal(a.ranks, b.ranks)) and a.recall_medr_meanr() == b.recall_medr_meanr() \
+                and a.mean_ap() == b.mean_ap()
+            ok = ok and same
+            if rank == 0:
+                print("rank_of_gt nv=%d: %s (median rank %.1f)" % (nv, "identical" if same else "MISMATCH",
+                                                                   b.recall_medr_meanr()[3]), flush=True)
         if k == 1000:
             rel = [sorted(set(np.random.default_rng(q).integers(0, nv, 300).tolist())) for q in range(nq)]
             s, i = avs.search_avs(shard, Q, k, weights=w, comm=distributed.GroupComm(), n_total=nv)

@@ -7,6 +7,7 @@
 // (fp32-valued inputs, fp64 products and sums) up to summation order, which is what makes the
 // returned top-k order and the ground-truth ranks identical to the reference's.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -196,6 +197,115 @@ score_f64_kernel(const double* __restrict__ a, int64_t nq, int64_t a_ld, const d
     }
 }
 
+// ---- the same matrix on the FP64 tensor-core path (DMMA) -------------------------------------------------------
+// mma.sync.m8n8k4.f64: one warp multiplies an 8 x 4 by a 4 x 8 fp64 tile (IEEE fused multiply-adds).  Block tile
+// 128 queries x 64 corpus rows, 4 warps of 64 x 32 (8 x 4 MMA tiles, 64 accumulators per thread): per k-step of 4 a
+// warp reads 12 doubles per lane for 32 MMAs -- 0.4 bytes of shared memory per FMA against 3 for the register-tiled
+// FMA kernel above, which is what held that one at 17 TFLOP/s.  Operands arrive through a 3-stage cp.async ring
+// (16-byte copies, zero-filled past the matrix edges); rows are padded to 20 doubles so that the 8 x 4 fragment loads
+// of a half-warp fall into 16 different bank pairs.
+constexpr int DM_BM = 128, DM_BN = 64, DM_BK = 16, DM_LD = DM_BK + 4, DM_STAGES = 3;
+constexpr int DM_STAGE_DOUBLES = (DM_BM + DM_BN) * DM_LD;
+constexpr int DM_SMEM_BYTES = DM_STAGES * DM_STAGE_DOUBLES * 8;
+
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem, int src_bytes) {
+  const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128, 2)
+score_f64_mma_kernel(const double* __restrict__ a, int64_t nq, int64_t a_ld, const double* __restrict__ b, int64_t nv,
+                     int64_t b_ld, int k, double alpha, double* __restrict__ out, int64_t out_ld) {
+  extern __shared__ __align__(16) double dm_smem[];
+  const int64_t q0 = static_cast<int64_t>(blockIdx.y) * DM_BM, v0 = static_cast<int64_t>(blockIdx.x) * DM_BN;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp >> 1, wn = warp & 1;                     // 2 x 2 warps of 64 x 32
+  const int n_kb = (k + DM_BK - 1) / DM_BK;
+
+  // one k-block of both operands -> stage: (128 + 64) rows x 8 sixteen-byte pieces, 12 pieces per thread
+  auto load_stage = [&](int kb, int stage) {
+    double* as = dm_smem + stage * DM_STAGE_DOUBLES;
+    double* bs = as + DM_BM * DM_LD;
+    const int k0 = kb * DM_BK;
+#pragma unroll
+    for (int it = 0; it < (DM_BM + DM_BN) * 8 / 128; ++it) {
+      const int piece = it * 128 + threadIdx.x;
+      const int row = piece >> 3, c2 = (piece & 7) * 2;        // two doubles at k0 + c2
+      const bool is_a = row < DM_BM;
+      const int64_t gr = is_a ? q0 + row : v0 + (row - DM_BM);
+      const int64_t n_rows = is_a ? nq : nv;
+      const double* base = is_a ? a : b;
+      const int64_t ld = is_a ? a_ld : b_ld;
+      int bytes = 0;
+      if (gr < n_rows) bytes = (k0 + c2 + 1 < k) ? 16 : ((k0 + c2 < k) ? 8 : 0);
+      const double* src = bytes ? base + gr * ld + k0 + c2 : base;
+      double* dst = (is_a ? as + row * DM_LD : bs + (row - DM_BM) * DM_LD) + c2;
+      cp_async_16(dst, src, bytes);
+    }
+  };
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < DM_STAGES - 1; ++s) {
+    if (s < n_kb) load_stage(s, s);
+    cp_async_commit();
+  }
+  for (int kb = 0; kb < n_kb; ++kb) {
+    cp_async_wait<DM_STAGES - 2>();
+    __syncthreads();                                           // stage kb has landed; stage kb-1 is free again
+    if (kb + DM_STAGES - 1 < n_kb) load_stage(kb + DM_STAGES - 1, (kb + DM_STAGES - 1) % DM_STAGES);
+    cp_async_commit();
+    const double* as = dm_smem + (kb % DM_STAGES) * DM_STAGE_DOUBLES + (wm * 64 + (lane >> 2)) * DM_LD + (lane & 3);
+    const double* bs = dm_smem + (kb % DM_STAGES) * DM_STAGE_DOUBLES + DM_BM * DM_LD + (wn * 32 + (lane >> 2)) * DM_LD +
+                       (lane & 3);
+#pragma unroll
+    for (int kk = 0; kk < DM_BK; kk += 4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) af[i] = as[i * 8 * DM_LD + kk];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = bs[j * 8 * DM_LD + kk];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_884(acc[i][j], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+  // C fragment: row = lane / 4, columns 2 * (lane % 4) + {0, 1}
+  const bool vec = (out_ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t q = q0 + wm * 64 + i * 8 + (lane >> 2);
+    if (q >= nq) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t v = v0 + wn * 32 + j * 8 + (lane & 3) * 2;
+      double* dst = out + q * out_ld + v;
+      if (vec && v + 1 < nv) {
+        *reinterpret_cast<double2*>(dst) = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
+      } else {
+        if (v < nv) dst[0] = alpha * acc[i][j][0];
+        if (v + 1 < nv) dst[1] = alpha * acc[i][j][1];
+      }
+    }
+  }
+}
+
 constexpr int PTM = 64, PTN = 64, PTK = 16;   // pairwise measures: 256 threads, 4 x 4 outputs each
 
 // ---- non-cosine measures of cal_error (evaluation.py:22-35): tiled pairwise distances on the CUDA cores --------
@@ -324,6 +434,22 @@ extern "C" int xmve_score_f64(const double* a, int64_t nq, int64_t a_ld, const d
   if (nq == 0 || nv == 0) return XMVE_OK;
   dim3 grid(static_cast<unsigned>((nv + TN - 1) / TN), static_cast<unsigned>((nq + TM - 1) / TM));
   if (grid.y > 65535) return fail(XMVE_ERR_LIMIT, "score_f64: more than %d query rows; chunk the call", 65535 * TM);
+  // FP64 tensor-core path: needs 16-byte aligned operand rows (cp.async); XMVE_F64_KERNEL=fma forces the FMA kernel
+  const bool aligned = aligned16(a) && aligned16(b) && a_ld % 2 == 0 && b_ld % 2 == 0;
+  const char* force = getenv("XMVE_F64_KERNEL");
+  if (aligned && !(force != nullptr && force[0] == 'f')) {
+    static bool attr_set[MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (dev < 0) return fail(XMVE_ERR_DEVICE, "score_f64: no current device");
+    if (!attr_set[dev]) {
+      XMVE_CUDA(cudaFuncSetAttribute(score_f64_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM_BYTES));
+      attr_set[dev] = true;
+    }
+    static_assert(DM_BM == TM && DM_BN == TN, "both fp64 kernels share one grid");
+    score_f64_mma_kernel<<<grid, 128, DM_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(a, nq, a_ld, b, nv, b_ld, k,
+                                                                                        alpha, out, out_ld);
+    return launch_status("score_f64_mma_kernel");
+  }
   score_f64_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, nq, a_ld, b, nv, b_ld, k, alpha, out,
                                                                        out_ld);
   return launch_status("score_f64_kernel");

@@ -410,7 +410,7 @@ def test_planted_neighbours_found_at_1m(X):
 
 
 # ---- exact ground-truth ranks without the score matrix (engine.rank_of_gt) -------------------
-def _planted_eval_set(X, nv=200_000, nq=600, d=128, sigma=4.5, seed=15):
+def _planted_eval_set(X, nv=200_000, nq=600, d=128, sigma=2.2, seed=15):
     V, Q, vid, cap, _ = X.synth.msrvtt_like(seed, nv, 1, d, sigma)
     return V, Q[:nq], vid, cap[:nq]
 
@@ -426,7 +426,7 @@ def test_rank_metrics_against_a_resident_corpus_equal_the_reference(X):
     stats = {}
     res = X.metrics.RankResult.from_store(store, torch.from_numpy(Q), t2v_gt, first_only=True, stats=stats)
     np.testing.assert_array_equal(res.ranks.cpu().numpy(), linas.gt_ranks(err, t2v_gt))       # every rank, exactly
-    assert res.recall_medr_meanr() == ref and 5.0 < ref[0] < 95.0
+    assert res.recall_medr_meanr() == ref and 2.0 < ref[0] < 98.0 and ref[4] > 10.0       # non-degenerate
     assert res.mean_ap() == linas.t2v_map(err, t2v_gt)
     assert X.metrics.eval_q2m_store(store, torch.from_numpy(Q), t2v_gt) == ref
     assert X.metrics.t2v_map_store(store, torch.from_numpy(Q), t2v_gt) == linas.t2v_map(err, t2v_gt)
@@ -461,7 +461,7 @@ def test_rank_of_gt_deep_fallback_and_multi_gt(X):
 
 def test_rank_of_gt_over_two_shards_and_two_spaces(X):
     dims, w = (96, 32), (0.7, 0.3)
-    V, Q, vid, cap = _planted_eval_set(X, nv=150_000, nq=300, d=sum(dims), sigma=5.0, seed=17)
+    V, Q, vid, cap = _planted_eval_set(X, nv=150_000, nq=300, d=sum(dims), sigma=2.5, seed=17)
     cut = 80_001
     shards = [X.engine.CorpusStore(cut, dims).add(torch.from_numpy(V[:cut])),
               X.engine.CorpusStore(len(V) - cut, dims, index_offset=cut).add(torch.from_numpy(V[cut:]))]

@@ -22,49 +22,66 @@ def search_avs(stores, queries, k=1000, weights=None, comm=None, n_total=None):
     return search_shards(stores, queries, k, weights=weights, comm=comm, n_total=n_total)
 
 
+class RelevantSets:
+    """Per-query relevant shot rows as a CSR on the device, built once and reused by every :func:`ap_at_k` call."""
+
+    def __init__(self, relevant, device=None):
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.nq = len(relevant)
+        sizes = np.fromiter((len(r) for r in relevant), dtype=np.int64, count=self.nq)
+        off = np.zeros(self.nq + 1, dtype=np.int64)
+        np.cumsum(sizes, out=off[1:])
+        self.n_entries = int(off[-1])
+        self.max_rel = int(sizes.max()) if self.nq else 0
+        self.off = torch.from_numpy(off).to(dev)
+        rel = np.concatenate([np.asarray(r, dtype=np.int64).reshape(-1) for r in relevant]) if self.n_entries else \
+            np.zeros(1, np.int64)
+        self.rel = torch.from_numpy(rel).to(dev)
+        self.device = dev
+
+
 def _list_ranks(idx, relevant, n_mem):
     """1-based position of every relevant row in its query's ranked list (``n_mem + 1`` if absent) as a CSR:
     returns ``(off int64 [nq+1], rank int32 [n_entries], device)``."""
     idx = idx if torch.is_tensor(idx) else torch.as_tensor(np.asarray(idx))
     dev = idx.device if idx.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    sets = relevant if isinstance(relevant, RelevantSets) else RelevantSets(relevant, dev)
     idx = idx.to(dev, torch.int64)
     nq, kk = idx.shape
-    assert len(relevant) == nq, "one relevant set per query"
-    sizes = np.fromiter((len(r) for r in relevant), dtype=np.int64, count=nq)
-    off = np.zeros(nq + 1, dtype=np.int64)
-    np.cumsum(sizes, out=off[1:])
-    off_d = torch.from_numpy(off).to(dev)
-    if int(off[-1]) == 0:
-        return off_d, torch.zeros(1, dtype=torch.int32, device=dev), dev
-    rel = torch.from_numpy(np.concatenate([np.asarray(r, dtype=np.int64).reshape(-1) for r in relevant])).to(dev)
+    assert sets.nq == nq, "one relevant set per query"
+    if sets.n_entries == 0:
+        return sets.off, torch.zeros(1, dtype=torch.int32, device=dev), dev
     idx = idx.contiguous() if idx.stride(1) != 1 else idx
-    rank = torch.empty(int(off[-1]), dtype=torch.int32, device=dev)
-    N.call("xmve_list_ranks", N.ptr(idx), nq, kk, idx.stride(0), N.ptr(off_d), N.ptr(rel), int(off[-1]), int(n_mem) + 1,
-           N.ptr(rank), N.stream_ptr())
-    return off_d, rank, dev
+    rank = torch.empty(sets.n_entries, dtype=torch.int32, device=dev)
+    N.call("xmve_list_ranks", N.ptr(idx), nq, kk, idx.stride(0), N.ptr(sets.off), N.ptr(sets.rel), sets.n_entries,
+           int(n_mem) + 1, N.ptr(rank), N.stream_ptr())
+    return sets.off, rank, dev
 
 
-def ap_at_k(idx, relevant, n_shots, k=None):
+def ap_at_k(idx, relevant, n_shots, k=None, on_device=False):
     """``APScorer(k).score`` of every query's ranked list against its relevant set, on the device.
 
-    ``idx`` int64 ``[nq, kk]`` ranked shot rows (``-1`` padded), ``relevant`` one sequence of shot rows per query,
-    ``n_shots`` the corpus size (the length of the full list the reference scorer would be given).  Relevant
-    shots that are not in the returned list lie beyond position ``kk`` and contribute nothing, exactly as in
-    ``basic/metric.py:36-44``; the denominator is the size of the relevant set.  Returns ``(ap float64 [nq], mAP)``
-    with ``mAP = np.mean(ap)`` (``util/metrics.py:75-79`` style).
+    ``idx`` int64 ``[nq, kk]`` ranked shot rows (``-1`` padded), ``relevant`` one sequence of shot rows per query
+    (or a prebuilt :class:`RelevantSets`), ``n_shots`` the corpus size (the length of the full list the reference
+    scorer would be given).  Relevant shots that are not in the returned list lie beyond position ``kk`` and
+    contribute nothing, exactly as in ``basic/metric.py:36-44``; the denominator is the size of the relevant set.
+    Returns ``(ap float64 [nq], mAP)`` with ``mAP = np.mean(ap)`` (``util/metrics.py:75-79`` style); with
+    ``on_device=True`` the AP vector stays a device tensor and no host synchronisation happens (``mAP`` is None).
     """
     N.require_device()
     nq, kk = idx.shape
     k = kk if k is None else min(int(k), kk)
-    off_d, rank, dev = _list_ranks(idx, relevant, n_shots)
+    sets = relevant if isinstance(relevant, RelevantSets) else RelevantSets(relevant, idx.device if
+                                                                            torch.is_tensor(idx) and idx.is_cuda else None)
+    off_d, rank, dev = _list_ranks(idx, sets, n_shots)
     ap = torch.zeros(nq, dtype=torch.float64, device=dev)
-    if nq == 0 or int(off_d[-1]) == 0:
-        out = ap.cpu().numpy()
-        return out, (np.mean(out) if nq else np.float64("nan"))
-    from .metrics import rank_metrics
-    rank_metrics(rank, off_d, nq, n_shots, False, k, max(len(r) for r in relevant), None, ap, None, None)
+    if nq and sets.n_entries:
+        from .metrics import rank_metrics
+        rank_metrics(rank, off_d, nq, n_shots, False, k, sets.max_rel, None, ap, None, None)
+    if on_device:
+        return ap, None
     out = ap.cpu().numpy()
-    return out, np.mean(out)
+    return out, (np.mean(out) if nq else np.float64("nan"))
 
 
 def write_run_file(path, query_ids, idx, scores, shot_ids, run_tag="xmve"):

@@ -598,8 +598,10 @@ class _Search:
             st["cap"] = cap
             st["pilot_m"] = m
             st["cand_count"] = [c[0] for c in cands]
-            st["rescored_per_query"] = sum(float((e[:, :cap] > float("-inf")).sum()) for e in exacts) / max(n_sub, 1) \
-                if all(torch.is_tensor(e) for e in exacts) else None
+            ar = torch.arange(cap, device=dev)
+            st["rescored_per_query"] = sum(
+                float(((ar[None, :] < c[0][:, None]) & (e[:, :cap] > float("-inf"))).sum())
+                for c, e in zip(cands, exacts)) / max(n_sub, 1)
             ph.mark("stats_bookkeeping")
         return s_, i_, cert, thr_next, over, n_bad, thr_sub
 

@@ -8,5 +8,5 @@
 * :mod:`.inference` ``compute_cirr_val_metrics`` with the signature of ``MultiFusion/src/inference.py:26-27`` (single
   composed query -> top-1 name).
 """
-from .scoring import build_index, cirr_metrics_from_features, name_rows, top1_name  # noqa: F401
+from .scoring import CirrEvaluator, build_index, cirr_metrics_from_features, name_rows, top1_name  # noqa: F401
 from . import inference, validate  # noqa: F401

@@ -21,17 +21,28 @@ __device__ __forceinline__ float key_float(uint32_t k) {
 }
 
 // j-th largest (1-based) of get(0..n); -inf if n < j.  All threads of the block must call it.
+// 4-pass radix select over the order-preserving float key.  Scores of one row share their sign and most exponent
+// bits, so in the first passes nearly every element falls into one or two bins: the histogram adds are
+// warp-aggregated (__match_any_sync: one atomicAdd per distinct bin and warp) instead of 32 serialised atomics on
+// the same shared-memory word.
 template <typename Get>
 __device__ float block_kth_largest_of(Get get, int64_t n, int j, uint32_t* hist, uint32_t* bcast) {
   if (j <= 0 || n < j) return -CUDART_INF_F;
   uint32_t prefix = 0, mask = 0;
   uint32_t remaining = static_cast<uint32_t>(j);
+  const int lane = threadIdx.x & 31;
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
     __syncthreads();
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint32_t k = float_key(get(i));
-      if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 0xffu], 1u);
+    for (int64_t base = threadIdx.x - lane; base < n; base += blockDim.x) {    // warp-uniform trip count
+      const int64_t i = base + lane;
+      int bin = -1;
+      if (i < n) {
+        const uint32_t k = float_key(get(i));
+        if ((k & mask) == prefix) bin = static_cast<int>((k >> shift) & 0xffu);
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);
+      if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], static_cast<uint32_t>(__popc(peers)));
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -258,6 +269,12 @@ select_topk_kernel(const double* __restrict__ score, const IdxT* __restrict__ id
   }
 }
 
+int pow2_ceil(int64_t x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
 // ---- two-round rescore: the pilot ------------------------------------------------------------------
 // Round one rescores each shard's m best approximate candidates exactly.  pilot_top extracts the (up to) m largest
 // of those exact scores per row, descending, -inf padded (the entry of the query's excluded item is skipped); the
@@ -304,39 +321,45 @@ pilot_top_kernel(const double* __restrict__ exact, const int32_t* __restrict__ i
   for (int i = threadIdx.x; i < m; i += blockDim.x) out[r * m + i] = i < n ? buf[i] : -CUDART_INF;
 }
 
-// lists [n_seg, rows, m] (descending per segment) -> bound[r] = round_down(kth largest of the union - eps), -inf when
-// the union holds fewer than k finite scores.  One warp per row: rank of every element by counting.
+// lists [n_seg, rows, m] -> bound[r] = round_down(kth largest of the union - eps), -inf when the union holds fewer
+// than k finite scores.  One segment (one shard): the list is already sorted, the answer is its k-th entry -- one warp
+// per row.  Several: one block per row sorts the union (at most 8192 values) in shared memory.
 __global__ void __launch_bounds__(256)
-pilot_bound_kernel(const double* __restrict__ lists, int n_seg, int64_t rows, int m, int k, float eps,
-                   const float* __restrict__ eps_dev, float* __restrict__ bound) {
-  const int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+pilot_bound_single_kernel(const double* __restrict__ lists, int64_t rows, int m, int k, float eps,
+                          const float* __restrict__ eps_dev, float* __restrict__ bound) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   if (eps_dev != nullptr) eps *= eps_dev[0];
+  const double kth = k <= m ? lists[r * m + (k - 1)] : -CUDART_INF;
+  bound[r] = kth > -CUDART_INF ? __double2float_rd(kth - static_cast<double>(eps)) : -CUDART_INF_F;
+}
+
+__global__ void __launch_bounds__(256)
+pilot_bound_kernel(const double* __restrict__ lists, int n_seg, int64_t rows, int m, int k, float eps,
+                   const float* __restrict__ eps_dev, int P, float* __restrict__ bound) {
+  extern __shared__ double pb_buf[];
+  const int64_t r = blockIdx.x;
+  if (eps_dev != nullptr) eps *= eps_dev[0];
   const int total = n_seg * m;
-  // the k-th largest value x: #{y > x} < k <= #{y >= x}
-  double kth = -CUDART_INF;
-  for (int base = 0; base < total; base += 32) {
-    const int i = base + lane;
-    double x = -CUDART_INF;
-    if (i < total) x = lists[(static_cast<int64_t>(i / m) * rows + r) * m + (i % m)];
-    int gt = 0, ge = 0;
-    for (int g = 0; g < n_seg; ++g) {
-      const double* seg = lists + (static_cast<int64_t>(g) * rows + r) * m;
-      // descending segment: binary search for the counts
-      int lo = 0, hi = m;                                      // first position with seg[p] <= x  -> #{y > x}
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (seg[mid] > x) lo = mid + 1; else hi = mid; }
-      gt += lo;
-      hi = m;                                                  // first position with seg[p] < x   -> #{y >= x}
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (seg[mid] >= x) lo = mid + 1; else hi = mid; }
-      ge += lo;
+  for (int i = threadIdx.x; i < P; i += blockDim.x)
+    pb_buf[i] = i < total ? lists[(static_cast<int64_t>(i / m) * rows + r) * m + (i % m)] : -CUDART_INF;
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < P; t += blockDim.x) {
+        const int o = t ^ stride;
+        if (o > t) {
+          const bool desc = (t & size) == 0;
+          const double a = pb_buf[t], b = pb_buf[o];
+          if (desc ? (b > a) : (a > b)) { pb_buf[t] = b; pb_buf[o] = a; }
+        }
+      }
+      __syncthreads();
     }
-    if (x > -CUDART_INF && gt < k && k <= ge) kth = x;
-    if (__any_sync(0xffffffffu, kth > -CUDART_INF)) break;
+  if (threadIdx.x == 0) {
+    const double kth = k <= total ? pb_buf[k - 1] : -CUDART_INF;
+    bound[r] = kth > -CUDART_INF ? __double2float_rd(kth - static_cast<double>(eps)) : -CUDART_INF_F;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) kth = fmax(kth, __shfl_xor_sync(0xffffffffu, kth, o));
-  if (lane == 0) bound[r] = kth > -CUDART_INF ? __double2float_rd(kth - static_cast<double>(eps)) : -CUDART_INF_F;
 }
 
 // ---- the error bound eps on the device (engine.measured_eps without a host round trip) ---------------------------
@@ -373,12 +396,6 @@ eps_bound_kernel(const float* __restrict__ q_resid, int n_space, int64_t nq, con
     }
     eps_out[0] = (e > 0.0 && e < CUDART_INF) ? __double2float_ru(e) : fallback;
   }
-}
-
-int pow2_ceil(int64_t x) {
-  int p = 1;
-  while (p < x) p <<= 1;
-  return p;
 }
 
 template <typename IdxT>
@@ -514,9 +531,17 @@ extern "C" int xmve_pilot_bound(const double* lists, int32_t n_seg, int64_t rows
   XMVE_DEVICE_OR_RETURN();
   XMVE_REQUIRE(lists && bound && n_seg >= 1 && rows >= 0 && m > 0 && k > 0, "pilot_bound: bad arguments");
   if (rows == 0) return XMVE_OK;
-  const int64_t blocks = (rows + 7) / 8;
-  pilot_bound_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      lists, n_seg, rows, m, k, eps, eps_dev, bound);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_seg == 1) {
+    pilot_bound_single_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, st>>>(lists, rows, m, k, eps, eps_dev,
+                                                                                       bound);
+    return launch_status("pilot_bound_single_kernel");
+  }
+  const int64_t total = static_cast<int64_t>(n_seg) * m;
+  if (total > 4096) return fail(XMVE_ERR_LIMIT, "pilot_bound: %lld pilot scores per row exceed 4096", (long long)total);
+  const int P = pow2_ceil(total);
+  pilot_bound_kernel<<<static_cast<unsigned>(rows), 256, P * sizeof(double), st>>>(lists, n_seg, rows, m, k, eps,
+                                                                                  eps_dev, P, bound);
   return launch_status("pilot_bound_kernel");
 }
 

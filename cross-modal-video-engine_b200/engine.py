@@ -470,6 +470,8 @@ def _segments(parts, comm):
 
 #: the pilot holds at most this many exact scores per query and shard (xmve_pilot_top)
 PILOT_MAX = 1000
+#: ... and the union of the pilots of all shards at most this many (xmve_pilot_bound sorts it in shared memory)
+PILOT_UNION_MAX = 4096
 
 
 class PendingSearch:
@@ -543,7 +545,7 @@ class _Search:
         ph.mark("filter")
         # 4: what needs an exact score
         m = kk if self.solo else min(kk, int(math.ceil(1.5 * kk / self.n_shards)) + 10)
-        if kk <= PILOT_MAX:
+        if kk <= PILOT_MAX and (self.solo or self.n_shards * m <= PILOT_UNION_MAX):
             # two rounds.  One: every shard rescores its m best approximate candidates; the k-th largest exact score
             # of the union of these pilots (kth1) is a lower bound on the true k-th best.  Two: only candidates whose
             # approximate score reaches kth1 - eps can still belong to the top-k.

@@ -208,10 +208,6 @@ constexpr int DM_BM = 128, DM_BN = 64, DM_BK = 16, DM_LD = DM_BK + 4, DM_STAGES 
 constexpr int DM_STAGE_DOUBLES = (DM_BM + DM_BN) * DM_LD;
 constexpr int DM_SMEM_BYTES = DM_STAGES * DM_STAGE_DOUBLES * 8;
 
-__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem, int src_bytes) {
-  const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(src_bytes) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -231,25 +227,38 @@ score_f64_mma_kernel(const double* __restrict__ a, int64_t nq, int64_t a_ld, con
   const int wm = warp >> 1, wn = warp & 1;                     // 2 x 2 warps of 64 x 32
   const int n_kb = (k + DM_BK - 1) / DM_BK;
 
-  // one k-block of both operands -> stage: (128 + 64) rows x 8 sixteen-byte pieces, 12 pieces per thread
+  // One k-block of both operands -> stage: (128 + 64) rows x 8 sixteen-byte pieces, 12 pieces per thread.  Piece
+  // `it` of a thread is row it * 16 + tid / 8 (A rows for it < 8, B rows after) at the thread's FIXED k offset
+  // c2 = 2 * (tid % 8): every address is a loop-invariant base plus it * (16 rows), so the producer costs a handful
+  // of instructions per piece.  (The first version recomputed row / matrix / pointer per piece: 1.3 G integer
+  // instructions against 1.1 G DMMAs, and the warps that feed the tensor pipe spent a third of their time there.)
+  const int r8 = threadIdx.x >> 3, c2 = (threadIdx.x & 7) * 2;
+  const double* a_src = a + (q0 + r8) * a_ld + c2;
+  const double* b_src = b + (v0 + r8) * b_ld + c2;
+  const int64_t a_step = 16 * a_ld, b_step = 16 * b_ld;
+  // pieces whose row lies inside the matrix: it < a_rows_it (A), it < b_rows_it (B)
+  int64_t a_it = (nq - q0 - r8 + 15) / 16, b_it = (nv - v0 - r8 + 15) / 16;
+  const int a_rows_it = static_cast<int>(a_it < 0 ? 0 : (a_it > 8 ? 8 : a_it));
+  const int b_rows_it = static_cast<int>(b_it < 0 ? 0 : (b_it > 4 ? 4 : b_it));
+  const uint32_t smem0 = static_cast<uint32_t>(__cvta_generic_to_shared(dm_smem)) + (r8 * DM_LD + c2) * 8;
   auto load_stage = [&](int kb, int stage) {
-    double* as = dm_smem + stage * DM_STAGE_DOUBLES;
-    double* bs = as + DM_BM * DM_LD;
     const int k0 = kb * DM_BK;
+    const int left = k - k0 - c2;                               // doubles of this thread's column pair inside k
+    const int kbytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
+    const uint32_t dst0 = smem0 + stage * DM_STAGE_DOUBLES * 8;
+    const double* pa = a_src + k0;
+    const double* pb = b_src + k0;
 #pragma unroll
-    for (int it = 0; it < (DM_BM + DM_BN) * 8 / 128; ++it) {
-      const int piece = it * 128 + threadIdx.x;
-      const int row = piece >> 3, c2 = (piece & 7) * 2;        // two doubles at k0 + c2
-      const bool is_a = row < DM_BM;
-      const int64_t gr = is_a ? q0 + row : v0 + (row - DM_BM);
-      const int64_t n_rows = is_a ? nq : nv;
-      const double* base = is_a ? a : b;
-      const int64_t ld = is_a ? a_ld : b_ld;
-      int bytes = 0;
-      if (gr < n_rows) bytes = (k0 + c2 + 1 < k) ? 16 : ((k0 + c2 < k) ? 8 : 0);
-      const double* src = bytes ? base + gr * ld + k0 + c2 : base;
-      double* dst = (is_a ? as + row * DM_LD : bs + (row - DM_BM) * DM_LD) + c2;
-      cp_async_16(dst, src, bytes);
+    for (int it = 0; it < 8; ++it) {
+      const int bytes = it < a_rows_it ? kbytes : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + it * 16 * DM_LD * 8),
+                   "l"(bytes ? pa + it * a_step : a), "r"(bytes) : "memory");
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int bytes = it < b_rows_it ? kbytes : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (DM_BM + it * 16) * DM_LD * 8),
+                   "l"(bytes ? pb + it * b_step : b), "r"(bytes) : "memory");
     }
   };
 

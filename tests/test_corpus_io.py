@@ -133,3 +133,52 @@ def test_cli_search_and_eval(tmp_path, capsys):
         assert " * mAP: {}".format(round(tup[5], 4)) in out
     saved = torch.load(str(tmp_path / "topk.pt"), weights_only=False)
     assert saved["idx"].shape == (len(Q), 10) and saved["video_ids"] == vid
+
+
+@pytest.mark.gpu
+def test_cli_eval_against_the_resident_store_when_spaces_are_fused(tmp_path, capsys):
+    """--dims/--weights: no error matrix is formed; the t2v lines come from exact ranks against the store and equal
+    the oracle's on the fused matrix."""
+    from cross_modal_video_engine_b200 import cli, synth
+    from oracle import linas
+    V, Q, vid, cap, _ = synth.msrvtt_like(93, 30000, 1, 96, 2.2)
+    Q, cap = Q[:200], cap[:200]
+    corpus_io.write_bigfile(str(tmp_path / "bf"), vid, V)
+    np.save(str(tmp_path / "q.npy"), Q)
+    (tmp_path / "cap.txt").write_text(" ".join(cap))
+    cli.main(["eval", "--corpus", str(tmp_path / "bf"), "--queries", str(tmp_path / "q.npy"), "--caption-ids",
+              str(tmp_path / "cap.txt"), "--dims", "64,32", "--weights", "0.7,0.3"])
+    out = capsys.readouterr().out
+    V64, Q64 = V.astype(np.float64), Q.astype(np.float64)
+    err = linas.fused_errors([V64[:, :64], V64[:, 64:]], [Q64[:, :64], Q64[:, 64:]], (0.7, 0.3))
+    _, t2v_gt = linas.get_gt(vid, cap)
+    ref = linas.eval_q2m(err, t2v_gt)
+    assert " * r_1_5_10, medr, meanr: {}".format([round(x, 1) for x in ref]) in out
+    assert " * mAP: {}".format(round(linas.t2v_map(err, t2v_gt), 4)) in out
+
+
+@pytest.mark.gpu
+def test_cli_composed_matches_the_reference_golden(tmp_path, capsys):
+    """`cli composed` = MultiFusion validate.py's main tail on files: the printed recalls and results_wo_attn.npy of
+    golden case 'a' (minted by the unmodified reference, oracle/make_golden_mf.py)."""
+    import json
+    from cross_modal_video_engine_b200 import cli, synth
+    from conftest import GOLDEN, load_golden
+    with open(os.path.join(GOLDEN, "mf_cirr.json")) as f:
+        rec = json.load(f)["cases"]["a"]
+    index, P, names, ref, tgt = synth.composed_retrieval(rec["seed"], rec["n_index"], rec["n_query"],
+                                                         frames=rec["frames"], sigma=rec["sigma"])
+    torch.save({"index_features": torch.from_numpy(index), "index_names": names}, str(tmp_path / "index.pt"))
+    torch.save({"predicted_features": torch.from_numpy(P), "reference_names": ref, "target_names": tgt},
+               str(tmp_path / "queries.pt"))
+    assert cli.main(["composed", "--index", str(tmp_path / "index.pt"), "--queries", str(tmp_path / "queries.pt"),
+                     "--out", str(tmp_path / "results_wo_attn")]) == 0
+    out = capsys.readouterr().out
+    m = rec["metrics"]
+    for name, val in zip(("group_recall_at1", "group_recall_at2", "group_recall_at3"), (-1, -1, -1)):
+        assert "%s = %r" % (name, val) in out
+    for name, val in zip(("recall_at1", "recall_at5", "recall_at10", "recall_at50"), m[3:]):
+        assert "%s = %r" % (name, val) in out
+    top = np.load(str(tmp_path / "results_wo_attn.npy"))
+    gold = load_golden("mf_cirr_a")["top100"]
+    assert (top != gold).mean() < 2e-3                           # identical up to fp32 ties of the reference's ranking

@@ -373,6 +373,35 @@ def test_score_f64_and_normalize(N):
     torch.testing.assert_close(out, -(qn @ vn.T), rtol=0, atol=1e-14)
 
 
+@pytest.mark.parametrize("j1,j2", [(1, 0), (10, 107), (200, 256), (257, 0), (60, 3000)])
+def test_row_kth_pivot_and_radix_paths_agree_with_a_sort(N, j1, j2):
+    """Small order statistics go through the pivot search (j <= 256), larger ones through the radix select; rows with
+    heavy ties, -inf padding, a constant row, +inf / NaN entries and short rows must all give the exact statistic."""
+    g = torch.Generator(device="cuda").manual_seed(41)
+    rows, cols = 64, 9000
+    x = 0.02 * torch.randn((rows, cols), generator=g, device="cuda") + 0.01
+    x[1] = 0.5                                                # constant row
+    x[2, ::2] = 0.125                                         # half of the row ties above everything else
+    x[3, 300:] = float("-inf")                                # a padded union list: 300 finite values
+    x[4, 5] = float("inf")
+    x[5, 7] = float("nan")
+    x[6] = torch.rand(cols, generator=g, device="cuda") ** 8  # heavy-tailed, far from Gaussian
+    x[7] = -torch.rand(cols, generator=g, device="cuda") ** 8 # bulk at the TOP
+    x[8, :50] = 3.0                                           # 50 exact ties on top of a Gaussian bulk
+    counts = torch.full((rows,), cols, dtype=torch.int32, device="cuda")
+    counts[9], counts[10], counts[11] = 700, 5, 0             # short rows
+    out = torch.empty(rows, device="cuda")
+    N.call("xmve_row_kth", N.ptr(x), rows, cols, cols, N.ptr(counts), j1, 0.0, None, j2, N.ptr(out), N.stream_ptr())
+    for r in range(rows):
+        if r == 5:
+            continue                                          # NaN: ordering follows the float key (radix path); not asserted
+        n = int(counts[r])
+        srt = torch.sort(x[r, :n], descending=True).values
+        a1 = srt[j1 - 1].item() if n >= j1 else float("-inf")
+        a2 = srt[j2 - 1].item() if (j2 > 0 and n >= j2) else float("-inf")
+        assert out[r].item() == max(a1, a2), (r, j1, j2)
+
+
 # ---- rank / metric kernels ------------------------------------------------------------------------------
 def _ap_reference(ranks, n_mem, k, first_only=False):
     """APScorer(k).score (basic/metric.py:25-46) from the 1-based ranks of the relevant entries."""

@@ -214,11 +214,36 @@ row_topj_kernel(const float* __restrict__ vals, int64_t cols, int64_t ld, const 
   __shared__ uint32_t hist[256];
   __shared__ uint32_t bcast[2];
   __shared__ int n_buf;
+  __shared__ PivotScratch piv;
   extern __shared__ float topj_buf[];
   const int64_t r = blockIdx.x;
   int64_t n = cols;
   if (counts != nullptr) n = min(static_cast<int64_t>(counts[r]), cols);
   const float* row = vals + r * ld;
+  // small J: the pivot search hands over every value above a pivot that at least J values exceed (<= 1024 of them);
+  // sort those and keep the first J
+  int c = 0;
+  if (J <= PV_JMAX && n >= J && block_pivot_survivors(row, n, J, piv, &c)) {
+    int Q = 1;
+    while (Q < c) Q <<= 1;
+    for (int i = c + threadIdx.x; i < Q; i += blockDim.x) piv.buf[i] = -CUDART_INF_F;
+    __syncthreads();
+    for (int size = 2; size <= Q; size <<= 1)
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int x = threadIdx.x; x < Q; x += blockDim.x) {
+          const int o = x ^ stride;
+          if (o > x) {
+            const bool desc = (x & size) == 0;
+            const float a = piv.buf[x], b = piv.buf[o];
+            if (desc ? (b > a) : (a > b)) { piv.buf[x] = b; piv.buf[o] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    for (int i = threadIdx.x; i < J; i += blockDim.x) out[r * J + i] = piv.buf[i];
+    return;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) n_buf = 0;
   const float t = block_kth_largest(row, n, J, hist, bcast);       // -inf when the row has fewer than J values
   __syncthreads();
@@ -227,9 +252,9 @@ row_topj_kernel(const float* __restrict__ vals, int64_t cols, int64_t ld, const 
     if (v > t) topj_buf[atomicAdd(&n_buf, 1)] = v;                  // strictly above the J-th largest: < J values
   }
   __syncthreads();
-  const int c = n_buf;
+  const int cnt = n_buf;
   const int have = static_cast<int>(min(static_cast<int64_t>(J), n));
-  for (int i = c + threadIdx.x; i < P; i += blockDim.x) topj_buf[i] = (i < have) ? t : -CUDART_INF_F;
+  for (int i = cnt + threadIdx.x; i < P; i += blockDim.x) topj_buf[i] = (i < have) ? t : -CUDART_INF_F;
   __syncthreads();
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {

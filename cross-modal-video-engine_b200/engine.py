@@ -29,6 +29,14 @@ from . import _native as N
 #: (search(eps=...) callers, NaN rows); the search itself uses :func:`measured_eps` (typically 3.5e-3 - 4e-3).
 EPS_X1 = 8.5e-3
 SMALL_NV = 16384
+#: multiples of eps subtracted from the sampled threshold kth(sample, j).  Round 1 used 2: "the k-th best exact score
+#: is at least kth_approx - eps, a row's approximate score at most eps above its exact one".  But j already carries a
+#: 5.5-sigma sampling slack (plan()): the j-th largest of the sample sits near corpus rank j * step (1 500 at C5), an
+#: order of magnitude below the k-th best, so the certificate kth_exact - eps >= thr holds without the extra margin
+#: (P(miss) ~ 1e-7 per row; a miss only costs a re-run of that row).  Dropping it cuts the candidate lists from
+#: 5 800 to 1 500 per query at C5 and from 2 350 to 1 200 at C4, where the FILTER epilogue's candidate path was
+#: measured at 24 % of the kernel (profiles/r2_filter_k640.md).
+THR_EPS_MARGIN = 0.0
 ROW_TOPJ_MAX = 4096
 _BM, _BN = 128, 256
 
@@ -482,6 +490,7 @@ class PendingSearch:
 
     def __init__(self, ctx):
         self._ctx = ctx
+        self._ctx_template = None
         self._done = ctx is None
         self.scores = self.idx = None
         self.reran = False                    # True once result() had to re-run rows (scores / idx were rewritten)
@@ -607,18 +616,30 @@ class _Search:
             ph.mark("stats_bookkeeping")
         return s_, i_, cert, thr_next, over, n_bad, thr_sub
 
-    def first_pass(self):
+    def first_pass(self, in_graph=False, flag_host=None):
+        self._cap0 = self.cap
         s_, i_, cert, thr_next, over, n_bad, thr_sub = self.run_pass(None)
         self.out_s[:, :self.k_eff] = s_
         self.out_i[:, :self.k_eff] = i_
         self._last = (cert, thr_next, over, thr_sub)
         if self.dev.type == "cuda":
-            self._flag = torch.empty((1,), dtype=torch.int32).pin_memory()
+            # (pinned memory is allocated outside a graph capture: GraphSearch passes its own buffer)
+            self._flag = torch.empty((1,), dtype=torch.int32).pin_memory() if flag_host is None else flag_host
             self._flag.copy_(n_bad, non_blocking=True)
-            self._event = torch.cuda.Event()
-            self._event.record()
+            self._event = None
+            if not in_graph:                                  # a captured event cannot be waited on: see replayed()
+                self._event = torch.cuda.Event()
+                self._event.record()
         else:
             self._flag, self._event = n_bad, None
+        self._thr0 = self.thr
+
+    def replayed(self):
+        """The captured first pass has just been replayed (GraphSearch): mark the point the host waits for."""
+        self.thr = self._thr0                                 # a re-run of the previous batch may have replaced it
+        self.cap = self._cap0                                 # ... or grown the candidate lists
+        self._event = torch.cuda.Event()
+        self._event.record()
 
     def resolve(self):
         """Wait for the first pass's certificate count; re-run (all ranks alike) the rows that missed it."""
@@ -676,6 +697,70 @@ class _Search:
                               "or candidate capacity; heavy score ties?)" % int(bad.numel()))
 
 
+class GraphSearch:
+    """A search of fixed shape captured ONCE into a CUDA graph and replayed per query batch.
+
+    The first pass of :func:`search_shards` never waits for the host and has static shapes for a given
+    ``(number of queries, k, weights, exclude yes/no)``: about 25 kernel launches and as many small allocations, which
+    cost the host ~0.4 ms -- more than the GPU needs for a handful of queries (online search, the 60-query AVS batch).
+    Replaying the captured graph costs ~10 us of host time.  The rare uncertified rows are re-run eagerly by
+    :meth:`PendingSearch.result`, exactly as without a graph.
+
+        gs = GraphSearch(store, n_queries=60, k=1000)
+        scores, idx = gs(queries)                 # or  p = gs(queries, defer=True); ...; p.result()
+
+    One shard per process without a process group (``comm``) is the tested configuration; the returned tensors are
+    the graph's static output buffers and are overwritten by the next call.
+    """
+
+    def __init__(self, stores, n_queries, k, weights=None, with_exclude=False, comm=None, n_total=None,
+                 small_nv=SMALL_NV):
+        self.stores = list(stores) if isinstance(stores, (list, tuple)) else [stores]
+        ref = self.stores[0]
+        self.dev = ref.device
+        self.nq, self.k = int(n_queries), int(k)
+        self.comm = comm or SoloComm()
+        self.q_in = torch.zeros((self.nq, ref.dtot), dtype=torch.float32, device=self.dev)
+        self.excl_in = torch.full((self.nq,), -1, dtype=torch.int64, device=self.dev) if with_exclude else None
+        kw = dict(weights=weights, exclude=self.excl_in, eps=None, small_nv=small_nv, stats=None, comm=self.comm,
+                  n_total=n_total)
+        with torch.cuda.device(self.dev):
+            # warm-up outside the capture: opt-in shared-memory attributes, the cached corpus residual, NCCL
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    _search_shards(self.stores, self.q_in, self.k, kw["weights"], kw["exclude"], None, small_nv, None,
+                                   self.comm, n_total).result()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._flag_host = torch.empty((1,), dtype=torch.int32).pin_memory()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._pending = _search_shards(self.stores, self.q_in, self.k, kw["weights"], kw["exclude"], None,
+                                               small_nv, None, self.comm, n_total, in_graph=True,
+                                               flag_host=self._flag_host)
+        self.scores, self.idx = self._pending.scores, self._pending.idx
+
+    def __call__(self, queries, exclude=None, defer=False):
+        q = queries if torch.is_tensor(queries) else torch.as_tensor(queries)
+        assert tuple(q.shape) == tuple(self.q_in.shape), "GraphSearch was captured for %s queries" % (self.q_in.shape,)
+        with torch.cuda.device(self.dev):
+            self.q_in.copy_(q, non_blocking=True)
+            if self.excl_in is not None:
+                e = torch.full((self.nq,), -1, dtype=torch.int64) if exclude is None else torch.as_tensor(exclude)
+                self.excl_in.copy_(e.to(torch.int64), non_blocking=True)
+            else:
+                assert exclude is None, "capture with with_exclude=True to pass exclusions"
+            self.graph.replay()
+            ctx = self._pending._ctx_template
+            ctx.replayed()
+            p = PendingSearch(ctx)
+            p.scores, p.idx = self.scores, self.idx
+        return p if defer else p.result()
+
+
 def _dv2_global(stores, comm):
     """max over ALL corpus rows (every shard of every rank) of the squared bf16 residual: device fp32 [1], cached per
     corpus state -- the one all-reduce it needs is paid when the corpus changes, not per search."""
@@ -700,7 +785,7 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
        all-reduced once per corpus state, the query side is identical on every rank).
     2. the largest scores of a ``step``-strided sample of each shard (a coarse K2 STORE pass sets a floor, a K2
        FILTER pass over the sample keeps what exceeds it); the top-J of every shard are gathered and the global
-       threshold is ``max(kth(union, j) - 2 eps, kth(union, j_cap))`` -- what one GPU would compute on the whole
+       threshold is ``max(kth(union, j) - THR_EPS_MARGIN * eps, kth(union, j_cap))`` -- what one GPU would compute on the whole
        corpus, so each shard appends only its share of the candidates.
     3. K2 FILTER over each shard (the score matrix never reaches HBM).
     4. exact fp64 rescore in two rounds: every shard rescores its best ``m`` approximate candidates; the pilots are
@@ -725,7 +810,8 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
     return pending if defer else pending.result()
 
 
-def _search_shards(stores, queries, k, weights, exclude, eps, small_nv, stats, comm, n_total):
+def _search_shards(stores, queries, k, weights, exclude, eps, small_nv, stats, comm, n_total, in_graph=False,
+                   flag_host=None):
     ref = stores[0]
     dev, n_space = ref.device, len(ref.dims)
     n_shards = len(stores) * comm.world
@@ -786,7 +872,7 @@ def _search_shards(stores, queries, k, weights, exclude, eps, small_nv, stats, c
             lists.append((s._sample(a_op, nq, pl["step"]), None))
             floor = torch.full_like(floor, float("-inf"))     # a complete list needs no floor
     if solo:
-        thr = _row_kth(lists[0][0], lists[0][1], pl["j"], 2.0, j_cap, eps_t)
+        thr = _row_kth(lists[0][0], lists[0][1], pl["j"], THR_EPS_MARGIN, j_cap, eps_t)
     else:
         tops = [_row_topj(sc, cnt, big_j) for sc, cnt in lists]
         if not tops:
@@ -796,7 +882,7 @@ def _search_shards(stores, queries, k, weights, exclude, eps, small_nv, stats, c
         per = u.shape[1] // comm.world
         floor = u.view(nq, comm.world, per)[:, :, -1].min(dim=1).values
         u.view(nq, comm.world, per)[:, :, -1] = float("-inf")
-        thr = _row_kth(u, None, pl["j"], 2.0, j_cap, eps_t)
+        thr = _row_kth(u, None, pl["j"], THR_EPS_MARGIN, j_cap, eps_t)
     # a two-level list that came out too short gives -inf (or a value below the floor): fall back to the coarse
     # floor, which ~0.4 % of the corpus exceeds -- far more than k rows, so it is below the k-th best score
     thr = torch.maximum(thr, floor - 2.0 * eps_t)
@@ -804,8 +890,9 @@ def _search_shards(stores, queries, k, weights, exclude, eps, small_nv, stats, c
     ph.mark("sample_threshold")
     search = _Search(stores, comm, k, k_eff, kk, wts, excl, eps_t, pl, a_op, q_raw, q_norm, nq, thr, out_s, out_i,
                      stats, ph)
-    search.first_pass()
+    search.first_pass(in_graph, flag_host)
     pending = PendingSearch(search)
+    pending._ctx_template = search
     pending.scores, pending.idx = out_s, out_i
     return pending
 

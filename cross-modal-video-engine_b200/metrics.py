@@ -38,17 +38,15 @@ def get_gt(video_ids, caption_ids):
 
 
 # ---------------------------------------------------------------------------------------------------
-def _csr(gts, n_query):
-    """list-of-lists / dict-by-row ground truth -> (offsets int64, ids int32, max per query)."""
-    counts = np.zeros(n_query, dtype=np.int64)
-    rows = []
-    for i in range(n_query):
-        g = gts[i]                       # dict: KeyError if a query has no entry, like the reference (:142)
-        counts[i] = len(g)
-        rows.append(g)
+def _csr(gts, n_query, dtype=np.int32):
+    """list-of-lists / dict-by-row ground truth -> (offsets int64, ids, max per query).  C-level iteration
+    (``map`` / ``chain``): 59 800 single-entry rows take ~3 ms instead of ~10 ms of Python loop."""
+    from itertools import chain
+    rows = [gts[i] for i in range(n_query)]          # dict: KeyError if a query has no entry, like the reference (:142)
+    counts = np.fromiter(map(len, rows), dtype=np.int64, count=n_query)
     off = np.zeros(n_query + 1, dtype=np.int64)
     np.cumsum(counts, out=off[1:])
-    ids = np.fromiter((x for g in rows for x in g), dtype=np.int32, count=int(off[-1]))
+    ids = np.fromiter(chain.from_iterable(rows), dtype=dtype, count=int(off[-1]))
     return off, ids, int(counts.max()) if n_query else 0
 
 
@@ -67,12 +65,8 @@ def rank_metrics(ranks, off, n_query, n_mem, first_only, ap_k, max_gt, best=None
 
 
 def _csr64(gts, n_query):
-    """:func:`_csr` with int64 ids (global corpus rows of a 10 M-row corpus still fit int32; shards' offsets may not)."""
-    counts = np.fromiter((len(gts[i]) for i in range(n_query)), dtype=np.int64, count=n_query)
-    off = np.zeros(n_query + 1, dtype=np.int64)
-    np.cumsum(counts, out=off[1:])
-    ids = np.fromiter((x for i in range(n_query) for x in gts[i]), dtype=np.int64, count=int(off[-1]))
-    return off, ids, int(counts.max()) if n_query else 0
+    """:func:`_csr` with int64 ids (global rows of a sharded corpus)."""
+    return _csr(gts, n_query, np.int64)
 
 
 def _device_matrix(scores):

@@ -469,3 +469,42 @@ def test_rank_of_gt_over_two_shards_and_two_spaces(X):
     V64, Q64 = V.astype(np.float64), Q.astype(np.float64)
     err = linas.fused_errors([V64[:, :96], V64[:, 96:]], [Q64[:, :96], Q64[:, 96:]], w)
     assert X.metrics.eval_q2m_store(shards, torch.from_numpy(Q), t2v_gt, weights=w) == linas.eval_q2m(err, t2v_gt)
+
+
+# ---- CUDA-graph replay of a fixed-shape search ---------------------------------------------------------------------
+def test_graph_search_replays_equal_the_eager_search(X):
+    """GraphSearch captures the sync-free first pass once; replays on NEW query batches (and new exclusions) must equal
+    the eager search, including a batch whose first pass misses certificates and is re-run eagerly."""
+    nv, d, nq, k = 120_000, 128, 48, 20
+    V = X.synth.gaussian(61, nv, d)
+    store = X.engine.CorpusStore(nv, (d,)).add(torch.from_numpy(V))
+    gs = X.engine.GraphSearch(store, nq, k, with_exclude=True)
+    for seed in (62, 63, 64):
+        Q = torch.from_numpy(X.synth.gaussian(seed, nq, d)).cuda()
+        excl = torch.randint(0, nv, (nq,), generator=torch.Generator().manual_seed(seed))
+        s_ref, i_ref = store.search(Q, k, exclude=excl)
+        s, i = gs(Q, exclude=excl)
+        assert torch.equal(i, i_ref) and torch.equal(s, s_ref)
+    p = gs(Q, exclude=excl, defer=True)                              # deferred resolution works on a replay, too
+    s, i = p.result()
+    assert torch.equal(i, i_ref) and not p.reran
+    # a batch that needs the re-run loop: near-duplicates of the queries sit on the sampling grid, so the sampled
+    # threshold comes out too high for some rows (same construction as test_search_rerun_*)
+    step = X.engine.plan(k, nv)["step"]
+    V2 = V.copy()
+    Qn = Q.cpu().numpy()
+    grid = np.random.default_rng(5).permutation(np.arange(0, nv, step))[: 30 * nq].reshape(nq, 30)
+    for qi in range(nq):
+        V2[grid[qi]] = Qn[qi] + 0.3 * np.random.default_rng(qi).standard_normal((30, d)).astype(np.float32)
+    store2 = X.engine.CorpusStore(nv, (d,)).add(torch.from_numpy(V2))
+    gs2 = X.engine.GraphSearch(store2, nq, k)
+    st = {}
+    s_ref, i_ref = store2.search(Q, k, stats=st)
+    p = gs2(Q, defer=True)
+    s, i = p.result()
+    assert torch.equal(i, i_ref) and torch.equal(s, s_ref)
+    assert p.reran == (st.get("reruns", 0) >= 1)
+    Q3 = torch.from_numpy(X.synth.gaussian(65, nq, d)).cuda()       # and the next replay is clean again
+    s3, i3 = gs2(Q3)
+    s_ref3, i_ref3 = store2.search(Q3, k)
+    assert torch.equal(i3, i_ref3) and torch.equal(s3, s_ref3)

@@ -37,6 +37,25 @@ def run(tag, nv, nq, d, k, reps=10):
         tag, ms, nq / ms * 1e3, flops / ms / 1e9, byts / ms / 1e6,
         {k_: round(v, 3) for k_, v in st["phases_ms"].items()}, float(st["cand_count"][0].float().mean()), st["eps"]), "rescored/row %.0f" % st["rescored_per_query"],
         flush=True)
+    if os.environ.get("XMVE_BENCH_GRAPH", "1") != "0":
+        # the same search replayed from a CUDA graph (engine.GraphSearch), resolved one step late
+        gs = engine.GraphSearch(store, nq, k)
+        prev = None
+        for _ in range(3):
+            gs(q)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            p = gs(q, defer=True)
+            if prev is not None:
+                prev.result()
+            prev = p
+        prev.result()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_g = e0.elapsed_time(e1) / reps
+        print("%s: CUDA-graph replay %.3f ms/search  %.0f queries/s" % (tag, ms_g, nq / ms_g * 1e3), flush=True)
+        del gs
     del store
     torch.cuda.empty_cache()
 

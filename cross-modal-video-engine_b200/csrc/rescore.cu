@@ -201,12 +201,21 @@ score_f64_kernel(const double* __restrict__ a, int64_t nq, int64_t a_ld, const d
 // mma.sync.m8n8k4.f64: one warp multiplies an 8 x 4 by a 4 x 8 fp64 tile (IEEE fused multiply-adds).  Block tile
 // 128 queries x 64 corpus rows, 4 warps of 64 x 32 (8 x 4 MMA tiles, 64 accumulators per thread): per k-step of 4 a
 // warp reads 12 doubles per lane for 32 MMAs -- 0.4 bytes of shared memory per FMA against 3 for the register-tiled
-// FMA kernel above, which is what held that one at 17 TFLOP/s.  Operands arrive through a 3-stage cp.async ring
-// (16-byte copies, zero-filled past the matrix edges); rows are padded to 20 doubles so that the 8 x 4 fragment loads
+// FMA kernel above, which is what held that one at 17 TFLOP/s.  Operands arrive through a cp.async ring
+// (16-byte copies, zero-filled past the matrix edges); rows are padded by 4 doubles so that the 8 x 4 fragment loads
 // of a half-warp fall into 16 different bank pairs.
-constexpr int DM_BM = 128, DM_BN = 64, DM_BK = 16, DM_LD = DM_BK + 4, DM_STAGES = 3;
-constexpr int DM_STAGE_DOUBLES = (DM_BM + DM_BN) * DM_LD;
-constexpr int DM_SMEM_BYTES = DM_STAGES * DM_STAGE_DOUBLES * 8;
+// Two shapes of the ring: <BK = 32, 2 stages> (default: half as many block barriers per flop; 2 x 54 KB per block, two
+// blocks per SM) and <BK = 16, 3 stages> (XMVE_F64_BK=16).
+constexpr int DM_BM = 128, DM_BN = 64;
+template <int BK, int STAGES>
+struct DmCfg {
+  static constexpr int LD = BK + 4;                            // (BK + 4) % 16 == 4: conflict-free fragment loads
+  static constexpr int STAGE_DOUBLES = (DM_BM + DM_BN) * LD;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;
+  static constexpr int PIECES = BK / 2;                        // 16-byte pieces per row and k-block
+  static constexpr int ROWS_PASS = 128 / PIECES;               // rows covered by the 128 threads in one pass
+  static constexpr int A_PASSES = DM_BM / ROWS_PASS, B_PASSES = DM_BN / ROWS_PASS;
+};
 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -218,28 +227,32 @@ __device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
+template <int DM_BK, int DM_STAGES>
 __global__ void __launch_bounds__(128, 2)
 score_f64_mma_kernel(const double* __restrict__ a, int64_t nq, int64_t a_ld, const double* __restrict__ b, int64_t nv,
                      int64_t b_ld, int k, double alpha, double* __restrict__ out, int64_t out_ld) {
+  using C = DmCfg<DM_BK, DM_STAGES>;
+  constexpr int DM_LD = C::LD, DM_STAGE_DOUBLES = C::STAGE_DOUBLES;
   extern __shared__ __align__(16) double dm_smem[];
   const int64_t q0 = static_cast<int64_t>(blockIdx.y) * DM_BM, v0 = static_cast<int64_t>(blockIdx.x) * DM_BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = warp >> 1, wn = warp & 1;                     // 2 x 2 warps of 64 x 32
   const int n_kb = (k + DM_BK - 1) / DM_BK;
 
-  // One k-block of both operands -> stage: (128 + 64) rows x 8 sixteen-byte pieces, 12 pieces per thread.  Piece
-  // `it` of a thread is row it * 16 + tid / 8 (A rows for it < 8, B rows after) at the thread's FIXED k offset
-  // c2 = 2 * (tid % 8): every address is a loop-invariant base plus it * (16 rows), so the producer costs a handful
-  // of instructions per piece.  (The first version recomputed row / matrix / pointer per piece: 1.3 G integer
+  // One k-block of both operands -> stage: (128 + 64) rows x BK/2 sixteen-byte pieces.  Piece `it` of a thread is
+  // row it * ROWS_PASS + tid / PIECES (A rows first, B rows after) at the thread's FIXED k offset
+  // c2 = 2 * (tid % PIECES): every address is a loop-invariant base plus it * (ROWS_PASS rows), so the producer costs
+  // a handful of instructions per piece.  (The first version recomputed row / matrix / pointer per piece: 1.3 G integer
   // instructions against 1.1 G DMMAs, and the warps that feed the tensor pipe spent a third of their time there.)
-  const int r8 = threadIdx.x >> 3, c2 = (threadIdx.x & 7) * 2;
+  constexpr int RP = C::ROWS_PASS;
+  const int r8 = threadIdx.x / C::PIECES, c2 = (threadIdx.x % C::PIECES) * 2;
   const double* a_src = a + (q0 + r8) * a_ld + c2;
   const double* b_src = b + (v0 + r8) * b_ld + c2;
-  const int64_t a_step = 16 * a_ld, b_step = 16 * b_ld;
+  const int64_t a_step = RP * a_ld, b_step = RP * b_ld;
   // pieces whose row lies inside the matrix: it < a_rows_it (A), it < b_rows_it (B)
-  int64_t a_it = (nq - q0 - r8 + 15) / 16, b_it = (nv - v0 - r8 + 15) / 16;
-  const int a_rows_it = static_cast<int>(a_it < 0 ? 0 : (a_it > 8 ? 8 : a_it));
-  const int b_rows_it = static_cast<int>(b_it < 0 ? 0 : (b_it > 4 ? 4 : b_it));
+  int64_t a_it = (nq - q0 - r8 + RP - 1) / RP, b_it = (nv - v0 - r8 + RP - 1) / RP;
+  const int a_rows_it = static_cast<int>(a_it < 0 ? 0 : (a_it > C::A_PASSES ? C::A_PASSES : a_it));
+  const int b_rows_it = static_cast<int>(b_it < 0 ? 0 : (b_it > C::B_PASSES ? C::B_PASSES : b_it));
   const uint32_t smem0 = static_cast<uint32_t>(__cvta_generic_to_shared(dm_smem)) + (r8 * DM_LD + c2) * 8;
   auto load_stage = [&](int kb, int stage) {
     const int k0 = kb * DM_BK;
@@ -249,15 +262,15 @@ score_f64_mma_kernel(const double* __restrict__ a, int64_t nq, int64_t a_ld, con
     const double* pa = a_src + k0;
     const double* pb = b_src + k0;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < C::A_PASSES; ++it) {
       const int bytes = it < a_rows_it ? kbytes : 0;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + it * 16 * DM_LD * 8),
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + it * RP * DM_LD * 8),
                    "l"(bytes ? pa + it * a_step : a), "r"(bytes) : "memory");
     }
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < C::B_PASSES; ++it) {
       const int bytes = it < b_rows_it ? kbytes : 0;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (DM_BM + it * 16) * DM_LD * 8),
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (DM_BM + it * RP) * DM_LD * 8),
                    "l"(bytes ? pb + it * b_step : b), "r"(bytes) : "memory");
     }
   };
@@ -451,12 +464,20 @@ extern "C" int xmve_score_f64(const double* a, int64_t nq, int64_t a_ld, const d
     const int dev = current_device();
     if (dev < 0) return fail(XMVE_ERR_DEVICE, "score_f64: no current device");
     if (!attr_set[dev]) {
-      XMVE_CUDA(cudaFuncSetAttribute(score_f64_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM_BYTES));
+      XMVE_CUDA(cudaFuncSetAttribute(score_f64_mma_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     DmCfg<32, 2>::SMEM_BYTES));
+      XMVE_CUDA(cudaFuncSetAttribute(score_f64_mma_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     DmCfg<16, 3>::SMEM_BYTES));
       attr_set[dev] = true;
     }
     static_assert(DM_BM == TM && DM_BN == TN, "both fp64 kernels share one grid");
-    score_f64_mma_kernel<<<grid, 128, DM_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(a, nq, a_ld, b, nv, b_ld, k,
-                                                                                        alpha, out, out_ld);
+    const char* bk = getenv("XMVE_F64_BK");
+    if (bk != nullptr && atoi(bk) == 16)
+      score_f64_mma_kernel<16, 3><<<grid, 128, DmCfg<16, 3>::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
+          a, nq, a_ld, b, nv, b_ld, k, alpha, out, out_ld);
+    else
+      score_f64_mma_kernel<32, 2><<<grid, 128, DmCfg<32, 2>::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
+          a, nq, a_ld, b, nv, b_ld, k, alpha, out, out_ld);
     return launch_status("score_f64_mma_kernel");
   }
   score_f64_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, nq, a_ld, b, nv, b_ld, k, alpha, out,

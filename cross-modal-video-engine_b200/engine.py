@@ -720,7 +720,7 @@ class GraphSearch:
         self.dev = ref.device
         self.nq, self.k = int(n_queries), int(k)
         self.comm = comm or SoloComm()
-        self.q_in = torch.zeros((self.nq, ref.dtot), dtype=torch.float32, device=self.dev)
+        self.q_in = torch.randn((self.nq, ref.dtot), dtype=torch.float32, device=self.dev)   # warm-up queries
         self.excl_in = torch.full((self.nq,), -1, dtype=torch.int64, device=self.dev) if with_exclude else None
         kw = dict(weights=weights, exclude=self.excl_in, eps=None, small_nv=small_nv, stats=None, comm=self.comm,
                   n_total=n_total)

@@ -363,8 +363,13 @@ pairwise_kernel(const double* __restrict__ a, int64_t nq, int64_t a_ld, const do
         for (int j = 0; j < 4; ++j) {
           if (MEASURE == XMVE_MEASURE_L1) {
             acc[i][j] += fabs(av[i] - bv[j]);
-          } else if (MEASURE == XMVE_MEASURE_L2) {
+          } else if (MEASURE == XMVE_MEASURE_L2 || MEASURE == XMVE_MEASURE_SQL2) {
             const double t = av[i] - bv[j];
+            acc[i][j] = fma(t, t, acc[i][j]);
+          } else if (MEASURE == XMVE_MEASURE_DOT) {
+            acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+          } else if (MEASURE == XMVE_MEASURE_ORDER) {
+            const double t = fmax(bv[j] - av[i], 0.0);
             acc[i][j] = fma(t, t, acc[i][j]);
           } else {
             acc[i][j] += fmin(av[i], bv[j]);
@@ -381,7 +386,7 @@ pairwise_kernel(const double* __restrict__ a, int64_t nq, int64_t a_ld, const do
       const int64_t q = q0 + ty * 4 + i, v = v0 + tx * 4 + j;
       if (q < nq && v < nv) {
         double f = acc[i][j];
-        if (MEASURE == XMVE_MEASURE_L2) f = sqrt(f);
+        if (MEASURE == XMVE_MEASURE_L2 || MEASURE == XMVE_MEASURE_ORDER) f = sqrt(f);
         if (MEASURE == XMVE_MEASURE_JACCARD) f = f / acc2[MEASURE == XMVE_MEASURE_JACCARD ? i : 0][j];
         out[q * out_ld + v] = alpha * f + beta;
       }
@@ -391,6 +396,59 @@ pairwise_kernel(const double* __restrict__ a, int64_t nq, int64_t a_ld, const do
 }  // namespace
 }  // namespace xmve
 
+namespace xmve {
+namespace {
+// Triplet ranking cost of a square score matrix (LINAS-engine/loss.py:112-153): block i owns row i and column i.
+//   cost_s [i, j] = max(0, margin + scores[i, j] - scores[i, i])   (compare the diagonal with its ROW:    v2t)
+//   cost_im[i, j] = max(0, margin + scores[i, j] - scores[j, j])   (compare the diagonal with its COLUMN: t2v)
+// with the diagonal cleared; max_violation keeps the largest entry of each row (cost_s) / column (cost_im).
+// out[0] += sum over the kept cost_s entries, out[1] += the same for cost_im (fp64 atomics).
+__global__ void __launch_bounds__(256)
+triplet_cost_kernel(const double* __restrict__ scores, int64_t n, int64_t ld, double margin, int max_violation,
+                    double* __restrict__ out) {
+  __shared__ double red[2][8];
+  const int64_t i = blockIdx.x;
+  const double dii = scores[i * ld + i];
+  double a_s = 0.0, a_im = 0.0;                                 // running sum or max (costs are >= 0)
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+    if (j == i) continue;
+    const double cs = fmax(margin + scores[i * ld + j] - dii, 0.0);                       // row i
+    const double cm = fmax(margin + scores[j * ld + i] - dii, 0.0);                       // column i: diag of column i
+    if (max_violation) { a_s = fmax(a_s, cs); a_im = fmax(a_im, cm); }
+    else { a_s += cs; a_im += cm; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double t_s = __shfl_xor_sync(0xffffffffu, a_s, o), t_im = __shfl_xor_sync(0xffffffffu, a_im, o);
+    if (max_violation) { a_s = fmax(a_s, t_s); a_im = fmax(a_im, t_im); }
+    else { a_s += t_s; a_im += t_im; }
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a_s; red[1][threadIdx.x >> 5] = a_im; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      if (max_violation) { a_s = fmax(a_s, red[0][w]); a_im = fmax(a_im, red[1][w]); }
+      else { a_s += red[0][w]; a_im += red[1][w]; }
+    }
+    atomicAdd(&out[0], a_s);
+    atomicAdd(&out[1], a_im);
+  }
+}
+}  // namespace
+}  // namespace xmve
+
+extern "C" int xmve_triplet_cost(const double* scores, int64_t n, int64_t ld, double margin, int max_violation,
+                                 double* out, void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  XMVE_REQUIRE(scores && out && n >= 0 && ld >= n, "triplet_cost: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  XMVE_CUDA(cudaMemsetAsync(out, 0, 2 * sizeof(double), st));
+  if (n == 0) return XMVE_OK;
+  triplet_cost_kernel<<<static_cast<unsigned>(n), 256, 0, st>>>(scores, n, ld, margin, max_violation, out);
+  return launch_status("triplet_cost_kernel");
+}
+
 extern "C" int xmve_pairwise_f64(const double* a, int64_t nq, int64_t a_ld, const double* b, int64_t nv, int64_t b_ld,
                                  int k, int measure, double alpha, double beta, double* out, int64_t out_ld,
                                  void* stream) {
@@ -398,7 +456,7 @@ extern "C" int xmve_pairwise_f64(const double* a, int64_t nq, int64_t a_ld, cons
   XMVE_DEVICE_OR_RETURN();
   XMVE_REQUIRE(a && b && out && nq >= 0 && nv >= 0 && k > 0 && a_ld >= k && b_ld >= k && out_ld >= nv,
                "pairwise_f64: bad arguments");
-  XMVE_REQUIRE(measure >= XMVE_MEASURE_L1 && measure <= XMVE_MEASURE_JACCARD, "pairwise_f64: unknown measure %d", measure);
+  XMVE_REQUIRE(measure >= XMVE_MEASURE_L1 && measure <= XMVE_MEASURE_ORDER, "pairwise_f64: unknown measure %d", measure);
   if (nq == 0 || nv == 0) return XMVE_OK;
   dim3 grid(static_cast<unsigned>((nv + PTN - 1) / PTN), static_cast<unsigned>((nq + PTM - 1) / PTM));
   if (grid.y > 65535) return fail(XMVE_ERR_LIMIT, "pairwise_f64: more than %d query rows; chunk the call", 65535 * PTM);
@@ -407,6 +465,12 @@ extern "C" int xmve_pairwise_f64(const double* a, int64_t nq, int64_t a_ld, cons
     pairwise_kernel<XMVE_MEASURE_L1><<<grid, 256, 0, st>>>(a, nq, a_ld, b, nv, b_ld, k, alpha, beta, out, out_ld);
   else if (measure == XMVE_MEASURE_L2)
     pairwise_kernel<XMVE_MEASURE_L2><<<grid, 256, 0, st>>>(a, nq, a_ld, b, nv, b_ld, k, alpha, beta, out, out_ld);
+  else if (measure == XMVE_MEASURE_SQL2)
+    pairwise_kernel<XMVE_MEASURE_SQL2><<<grid, 256, 0, st>>>(a, nq, a_ld, b, nv, b_ld, k, alpha, beta, out, out_ld);
+  else if (measure == XMVE_MEASURE_DOT)
+    pairwise_kernel<XMVE_MEASURE_DOT><<<grid, 256, 0, st>>>(a, nq, a_ld, b, nv, b_ld, k, alpha, beta, out, out_ld);
+  else if (measure == XMVE_MEASURE_ORDER)
+    pairwise_kernel<XMVE_MEASURE_ORDER><<<grid, 256, 0, st>>>(a, nq, a_ld, b, nv, b_ld, k, alpha, beta, out, out_ld);
   else
     pairwise_kernel<XMVE_MEASURE_JACCARD><<<grid, 256, 0, st>>>(a, nq, a_ld, b, nv, b_ld, k, alpha, beta, out, out_ld);
   return launch_status("pairwise_kernel");

@@ -126,17 +126,25 @@ __device__ bool block_pivot_survivors(const float* __restrict__ row, int64_t n, 
   for (int it = 0; it < 16; ++it) {
     if (threadIdx.x == 0) sc.n_surv = 0;
     __syncthreads();
-    int c = 0;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const float x = row[i];
-      if (x > p) {
-        ++c;
-        const int slot = atomicAdd(&sc.n_surv, 1);                     // survivors only: a few hundred adds per row
-        if (slot < PV_CAP) sc.buf[slot] = x;
+    // warp-aggregated compaction: one shared-memory add per warp and 32 elements, whatever the number of survivors
+    // (truncated candidate lists, where most of the row survives a low pivot, made per-survivor adds the slow part)
+    for (int64_t base = threadIdx.x - lane; base < n; base += blockDim.x) {
+      const int64_t i = base + lane;
+      const float x = i < n ? row[i] : -CUDART_INF_F;
+      const bool hit = x > p;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m != 0) {
+        int pos = 0;
+        if (lane == 0) pos = atomicAdd(&sc.n_surv, __popc(m));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (hit) {
+          const int slot = pos + __popc(m & ((1u << lane) - 1u));
+          if (slot < PV_CAP) sc.buf[slot] = x;
+        }
       }
     }
     __syncthreads();
-    c = sc.n_surv;
+    const int c = sc.n_surv;
     __syncthreads();
     if (c >= j_max && c <= PV_CAP) { *n_out = c; return true; }
     if (c < j_max) { hi = p; c_hi = fmaxf(static_cast<float>(c), 0.5f); }

@@ -220,9 +220,22 @@ XMVE_API int xmve_score_f64(const double* a, int64_t nq, int64_t a_ld, const dou
  * 'l1' / 'l2' / 'euclidean': alpha = 1, beta = 0; 'l1_norm' / 'l2_norm': alpha = -1/k, beta = -1; 'jaccard': alpha = -1.
  * CUDA-core kernel (ALU-bound); at most 65535 * 64 query rows per call.
  */
-enum { XMVE_MEASURE_L1 = 0, XMVE_MEASURE_L2 = 1, XMVE_MEASURE_JACCARD = 2 };
+enum { XMVE_MEASURE_L1 = 0, XMVE_MEASURE_L2 = 1, XMVE_MEASURE_JACCARD = 2,
+       /* the similarity functions of the training loss (LINAS-engine/loss.py:7-73) */
+       XMVE_MEASURE_SQL2 = 3,   /* sum_i (a_i - b_i)^2           (euclidean_sim / L2_sim / L2_sim_norm: no root) */
+       XMVE_MEASURE_DOT = 4,    /* sum_i a_i * b_i                (cosine_sim on already normalised rows)        */
+       XMVE_MEASURE_ORDER = 5   /* sqrt(sum_i max(b_i - a_i, 0)^2) (order_sim)                                  */ };
 XMVE_API int xmve_pairwise_f64(const double* a, int64_t nq, int64_t a_ld, const double* b, int64_t nv, int64_t b_ld,
                       int k, int measure, double alpha, double beta, double* out, int64_t out_ld, void* stream);
+
+/* ---- triplet ranking cost of a batch score matrix (LINAS-engine/loss.py:112-153, forward value only) ------------
+ * scores fp64 [n, n] = sim(im, s) (xmve_pairwise_f64).  With the diagonal cleared,
+ *   out[0] = sum of cost_s  = max(0, margin + scores[i, j] - scores[i, i])  (max_violation: of each ROW's maximum)
+ *   out[1] = sum of cost_im = max(0, margin + scores[i, j] - scores[j, j])  (max_violation: of each COLUMN's maximum)
+ * out: DEVICE double[2] (zeroed by the call).  loss.py:147-150: 'sum' adds them, 'mean' divides by n*n (or n).
+ */
+XMVE_API int xmve_triplet_cost(const double* scores, int64_t n, int64_t ld, double margin, int max_violation,
+                      double* out, void* stream);
 
 /* ---- K4: bit-exact rank / metric kernels --------------------------------------------------------
  * errors is the caller's [n_row, n_col] matrix (fp32/fp64, smaller = better, as cal_error returns).

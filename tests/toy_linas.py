@@ -84,3 +84,18 @@ def loaders(style, device="cpu"):
     vid = Loader(V, vid_ids, 1, batch=7, device=device)
     txt = Loader(Q, cap_ids, 2, batch=11, support=S if style == "GT" else None, device=device)
     return vid, txt
+
+
+# ---- a seeded batch for the triplet ranking loss (oracle/make_golden_loss.py, tests/test_loss.py) ------------------
+#: every `measure` loss.TripletLoss knows (:96-109); False selects cosine_sim
+LOSS_MEASURES = [False, 'order', 'euclidean', 'jaccard', 'l1', 'l2', 'l1_norm', 'l2_norm']
+
+
+def loss_batch(n=37, dim=48):
+    """(s, im): l2-normalised caption / video embeddings of one training batch, caption i paired with video i."""
+    g = torch.Generator().manual_seed(7)
+    im = torch.randn((n, dim), generator=g)
+    s = im + 2.0 * torch.randn((n, dim), generator=g)          # noisy enough for many margin violations
+    im = im / im.norm(dim=1, keepdim=True)
+    s = s / s.norm(dim=1, keepdim=True)
+    return s, im

@@ -690,12 +690,19 @@ def bench_c4(ctx, args, steps, warmup):
     target_host = target.cpu()
     torch.cuda.synchronize()
     filt_events, unhook = ctx.hook(lambda name, a: name == "xmve_score_filter" and a[6] == 1)
-    step_device, finish_device = pipelined(
-        lambda: distributed.sharded_search(store, P, k, exclude=reference, n_total=nv, defer=True))
+    # one GPU: the fixed-shape search is captured once into a CUDA graph and replayed (engine.GraphSearch): ~25 launches
+    # per step would otherwise cost the host more than they cost the GPU
+    gs = engine.GraphSearch(store, nq, k, with_exclude=True) if world == 1 else None
+
+    def search(q):
+        if gs is not None:
+            return gs(q, exclude=reference, defer=True)
+        return distributed.sharded_search(store, q, k, exclude=reference, n_total=nv, defer=True)
+    step_device, finish_device = pipelined(lambda: search(P))
 
     def step_e2e():
-        q = P_host.to(device, non_blocking=True)
-        p = distributed.sharded_search(store, q, k, exclude=reference, n_total=nv, defer=True)
+        q = P_host if gs is not None else P_host.to(device, non_blocking=True)   # the graph copies into its own buffer
+        p = search(q)
         out_i_host.copy_(p.idx, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         s, i = p.result()
@@ -736,7 +743,7 @@ def bench_c4(ctx, args, steps, warmup):
     st = {}
     distributed.sharded_search(store, P, k, exclude=reference, n_total=nv, stats=st)
     digest = result_digest(s_fin, i_fin) if rank == 0 else None
-    del store
+    del store, gs
     torch.cuda.empty_cache()
     if rank != 0:
         return None
@@ -750,6 +757,7 @@ def bench_c4(ctx, args, steps, warmup):
         "dtype": "bf16 (tensor-core filter) + f64 (exact rescore)", "data": "synthetic, generated on device, seeded",
         "config": {"workload": WORKLOADS["c4"], "nv": nv, "nq": nq, "dim": d, "frames": frames, "k": k,
                    "parallelism": "index rows sharded over %d GPU(s), queries replicated" % world,
+                   "cuda_graph": gs is not None,
                    "l2": "1.3 GB bf16 index operand per step exceeds the 126 MB L2"},
         "e2e": {"value": nq / (ms_e2e / steps * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4,
                 "d2h_bytes_per_step": nq * k * 8, "note": "unit-norm fused query features in, top-100 rows + recalls out"},
@@ -807,7 +815,11 @@ def bench_c3(ctx, args, steps, warmup):
     torch.cuda.synchronize()
     filt_events, unhook = ctx.hook(lambda name, a: name == "xmve_score_filter" and a[6] == 1)
 
+    gs = engine.GraphSearch(store, nq, k) if world == 1 else None          # CUDA-graph replay on one GPU (see C4)
+
     def search(q):
+        if gs is not None:
+            return gs(q, defer=True)
         return engine.search_shards([store], q, k, comm=comm, n_total=nv, defer=True)
 
     def enqueue():
@@ -817,7 +829,7 @@ def bench_c3(ctx, args, steps, warmup):
     step_device, finish_device = pipelined(enqueue)
 
     def step_e2e():
-        q = Q_host.to(device, non_blocking=True)
+        q = Q_host if gs is not None else Q_host.to(device, non_blocking=True)
         p = search(q)
         ap, _ = avs.ap_at_k(p.idx, sets, nv, k, on_device=True)
         out_i_host.copy_(p.idx, non_blocking=True)
@@ -852,7 +864,7 @@ def bench_c3(ctx, args, steps, warmup):
     st = {}
     engine.search_shards([store], Q, k, comm=comm, n_total=nv, stats=st)
     digest = result_digest(s_fin, i_fin) if rank == 0 else None
-    del store
+    del store, gs
     torch.cuda.empty_cache()
     if rank != 0:
         return None
@@ -866,6 +878,7 @@ def bench_c3(ctx, args, steps, warmup):
         "dtype": "bf16 (tensor-core filter) + f64 (exact rescore)", "data": "synthetic, generated on device, seeded",
         "config": {"workload": WORKLOADS["c3"], "nv": nv, "nq": nq, "dim": d, "k": k,
                    "parallelism": "shots sharded over %d GPU(s), queries replicated" % world,
+                   "cuda_graph": gs is not None,
                    "l2": "4.4 GB bf16 corpus operand per step exceeds the 126 MB L2"},
         "e2e": {"value": nq / (ms_e2e / steps * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4,
                 "d2h_bytes_per_step": nq * k * 8 + nq * 8, "note": "raw queries in, top-1000 shot rows + AP@1000 out"},

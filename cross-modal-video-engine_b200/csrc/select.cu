@@ -81,7 +81,7 @@ __device__ __forceinline__ float inv_normal_tail(float p) {           // z with 
 // All 256 threads call it.  On success sc.buf[0 .. *n_out) holds every value above the pivot (>= j_max of them).
 __device__ bool block_pivot_survivors(const float* __restrict__ row, int64_t n, int j_max, PivotScratch& sc, int* n_out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (n <= PV_CAP) {                                                   // short row: everything is a survivor
+  if (n <= max(256, 3 * j_max) && n <= PV_CAP) {                       // short row: everything is a survivor
     int nan = 0;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
       const float x = row[i];
@@ -119,6 +119,8 @@ __device__ bool block_pivot_survivors(const float* __restrict__ row, int64_t n, 
   if (weird || nf < j_max) return false;
   const float mean = sum / nf, sd = sqrtf(fmaxf(sq / nf - mean * mean, 0.f));
   const float target = fminf(2.5f * j_max, 0.5f * (j_max + PV_CAP));   // survivors aimed at
+  const int c_ok = min(PV_CAP, max(384, 4 * j_max));                   // ... accepted (they are sorted afterwards)
+  int c_best = 0;                                                      // a larger acceptable set seen on the way
   float lo = -CUDART_INF_F, hi = mx, c_lo = static_cast<float>(nf), c_hi = 0.5f;   // #{x > lo} >= j_max > #{x > hi}
   float p = mean + sd * inv_normal_tail(fminf(0.5f, target / nf));
   if (!(p < hi)) p = mean;                                             // degenerate spread
@@ -146,7 +148,8 @@ __device__ bool block_pivot_survivors(const float* __restrict__ row, int64_t n, 
     __syncthreads();
     const int c = sc.n_surv;
     __syncthreads();
-    if (c >= j_max && c <= PV_CAP) { *n_out = c; return true; }
+    if (c >= j_max && c <= c_ok) { *n_out = c; return true; }
+    c_best = (c >= j_max && c <= PV_CAP) ? c : 0;                      // usable if the search cannot do better
     if (c < j_max) { hi = p; c_hi = fmaxf(static_cast<float>(c), 0.5f); }
     else { lo = p; c_lo = static_cast<float>(c); }
     float next;
@@ -160,9 +163,13 @@ __device__ bool block_pivot_survivors(const float* __restrict__ row, int64_t n, 
       step *= 2.f;
       if (!(next > mean - 64.f * sd - 1e-30f)) return false;
     }
-    if (!(next > lo && next < hi)) return false;                       // brackets are adjacent floats: massive ties
+    if (!(next > lo && next < hi)) {                                   // brackets are adjacent floats: massive ties
+      if (c_best) { *n_out = c_best; return true; }                    // (the buffer still holds that probe's survivors)
+      return false;
+    }
     p = next;
   }
+  if (c_best) { *n_out = c_best; return true; }
   return false;
 }
 
@@ -613,7 +620,9 @@ int launch_select(const double* score, const IdxT* idx, int64_t rows, int64_t co
     XMVE_CUDA(cudaFuncSetAttribute(select_topk_kernel<IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_bytes[dev] = smem_bytes;
   }
-  select_topk_kernel<IdxT><<<static_cast<unsigned>(rows), 512, smem_bytes, st>>>(
+  // small sorts: 256 threads, so that eight rows are resident per SM (the kernel is a chain of short dependent phases)
+  const int threads = pmax <= 2048 ? 256 : 512;
+  select_topk_kernel<IdxT><<<static_cast<unsigned>(rows), threads, smem_bytes, st>>>(
       score, idx, cols, counts, idx_offset, exclude, k, thr, eps, eps_dev, bound, overflow, seg, pmax, out_score,
       out_idx, out_valid, cert, thr_next, n_uncertified);
   return launch_status("select_topk_kernel");

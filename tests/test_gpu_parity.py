@@ -508,3 +508,20 @@ def test_graph_search_replays_equal_the_eager_search(X):
     s3, i3 = gs2(Q3)
     s_ref3, i_ref3 = store2.search(Q3, k)
     assert torch.equal(i3, i_ref3) and torch.equal(s3, s_ref3)
+
+
+def test_deep_lists_over_two_shards(X):
+    """k = 2000 over a 22 k-row corpus cut into two shards (the sharded path asked row_topj for more
+    than its 4096-value capacity and raised XMVE_ERR_LIMIT; lists deeper than 1000 take the one-round rescore)."""
+    nv, d, nq, k = 22_000, 96, 9, 2000
+    V, Q = X.synth.gaussian(71, nv, d), X.synth.gaussian(72, nq, d)
+    cut = 10_001
+    shards = [X.engine.CorpusStore(cut, (d,)).add(torch.from_numpy(V[:cut])),
+              X.engine.CorpusStore(nv - cut, (d,), index_offset=cut).add(torch.from_numpy(V[cut:]))]
+    s, i = X.engine.search_shards(shards, torch.from_numpy(Q), k)
+    ref_idx, ref_s = _oracle_topk(V, Q, k)
+    np.testing.assert_array_equal(i.cpu().numpy(), ref_idx)
+    np.testing.assert_allclose(s.cpu().numpy(), ref_s, rtol=0, atol=1e-12)
+    one = X.engine.CorpusStore(nv, (d,)).add(torch.from_numpy(V))
+    s1, i1 = one.search(torch.from_numpy(Q), k)
+    assert torch.equal(i1, i) and torch.equal(s1, s)

@@ -53,6 +53,7 @@ SIGNATURES = {
     "xmve_row_topj": [_p, _l, _l, _l, _p, _i32, _p, _p],
     "xmve_normalize_f64": [_p, _i, _l, _i, _l, _p, _l, _i, _p],
     "xmve_score_f64": [_p, _l, _l, _p, _l, _l, _i, _d, _p, _l, _p],
+    "xmve_score_f64_fused": [_p, _l, _l, _p, _l, _l, _i, _d, _d, _i, _p, _l, _p],
     "xmve_pairwise_f64": [_p, _l, _l, _p, _l, _l, _i, _i, _d, _d, _p, _l, _p],
     "xmve_triplet_cost": [_p, _l, _l, _d, _i, _p, _p],
     "xmve_gt_ranks": [_p, _i, _l, _l, _l, _i, _p, _p, _l, _l, _i32, _p, _p],
@@ -76,7 +77,7 @@ lib.xmve_last_error.restype = C.c_char_p
 launch_count = 0
 _LAUNCHES = {"xmve_prepare_rows": 1, "xmve_score_store": 1, "xmve_score_filter": 1, "xmve_row_kth": 1,
              "xmve_rescore": 1, "xmve_pilot_top": 1, "xmve_pilot_bound": 1, "xmve_eps_bound": 1, "xmve_merge_topk_packed": 1, "xmve_select_topk_i32": 1, "xmve_select_topk_i64": 1, "xmve_row_topj": 1, "xmve_normalize_f64": 1,
-             "xmve_score_f64": 1, "xmve_pairwise_f64": 1, "xmve_triplet_cost": 1, "xmve_gt_ranks": 1, "xmve_rank_metrics": 1, "xmve_list_ranks": 1, "xmve_count_before": 1, "xmve_count_band_f64": 1, "xmve_norm_score": 3, "xmve_fuse_accumulate": 1}
+             "xmve_score_f64": 1, "xmve_score_f64_fused": 1, "xmve_pairwise_f64": 1, "xmve_triplet_cost": 1, "xmve_gt_ranks": 1, "xmve_rank_metrics": 1, "xmve_list_ranks": 1, "xmve_count_before": 1, "xmve_count_band_f64": 1, "xmve_norm_score": 3, "xmve_fuse_accumulate": 1}
 
 
 def call(name, *args):

@@ -230,7 +230,9 @@ __device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
 template <int DM_BK, int DM_STAGES>
 __global__ void __launch_bounds__(128, 2)
 score_f64_mma_kernel(const double* __restrict__ a, int64_t nq, int64_t a_ld, const double* __restrict__ b, int64_t nv,
-                     int64_t b_ld, int k, double alpha, double* __restrict__ out, int64_t out_ld) {
+                     int64_t b_ld, int k, double alpha, double w, int fuse, double* __restrict__ out, int64_t out_ld) {
+  // fuse: 0 -> out = alpha * S;  1 -> out = w * (alpha * S);  2 -> out = out + w * (alpha * S), every product and sum
+  // rounded on its own (what NumPy's `acc + w * e` does): the multi-space fusion of section 8a row F in the epilogue
   using C = DmCfg<DM_BK, DM_STAGES>;
   constexpr int DM_LD = C::LD, DM_STAGE_DOUBLES = C::STAGE_DOUBLES;
   extern __shared__ __align__(16) double dm_smem[];
@@ -318,11 +320,21 @@ score_f64_mma_kernel(const double* __restrict__ a, int64_t nq, int64_t a_ld, con
     for (int j = 0; j < 4; ++j) {
       const int64_t v = v0 + wn * 32 + j * 8 + (lane & 3) * 2;
       double* dst = out + q * out_ld + v;
+      double e0 = __dmul_rn(alpha, acc[i][j][0]), e1 = __dmul_rn(alpha, acc[i][j][1]);
+      if (fuse != 0) {
+        e0 = __dmul_rn(w, e0);
+        e1 = __dmul_rn(w, e1);
+      }
       if (vec && v + 1 < nv) {
-        *reinterpret_cast<double2*>(dst) = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
+        if (fuse == 2) {
+          const double2 old = *reinterpret_cast<const double2*>(dst);
+          e0 = __dadd_rn(old.x, e0);
+          e1 = __dadd_rn(old.y, e1);
+        }
+        *reinterpret_cast<double2*>(dst) = make_double2(e0, e1);
       } else {
-        if (v < nv) dst[0] = alpha * acc[i][j][0];
-        if (v + 1 < nv) dst[1] = alpha * acc[i][j][1];
+        if (v < nv) dst[0] = fuse == 2 ? __dadd_rn(dst[0], e0) : e0;
+        if (v + 1 < nv) dst[1] = fuse == 2 ? __dadd_rn(dst[1], e1) : e1;
       }
     }
   }
@@ -511,10 +523,10 @@ extern "C" int xmve_rescore(const float* q_raw, int64_t nq, int64_t q_ld, const 
   return launch_status("rescore_kernel");
 }
 
-extern "C" int xmve_score_f64(const double* a, int64_t nq, int64_t a_ld, const double* b, int64_t nv, int64_t b_ld,
-                              int k, double alpha, double* out, int64_t out_ld, void* stream) {
-  using namespace xmve;
-  XMVE_DEVICE_OR_RETURN();
+namespace xmve {
+namespace {
+int launch_score_f64(const double* a, int64_t nq, int64_t a_ld, const double* b, int64_t nv, int64_t b_ld, int k,
+                     double alpha, double w, int fuse, double* out, int64_t out_ld, void* stream) {
   XMVE_REQUIRE(a && b && out && nq >= 0 && nv >= 0 && k > 0 && a_ld >= k && b_ld >= k && out_ld >= nv,
                "score_f64: bad arguments");
   if (nq == 0 || nv == 0) return XMVE_OK;
@@ -538,13 +550,31 @@ extern "C" int xmve_score_f64(const double* a, int64_t nq, int64_t a_ld, const d
     const char* bk = getenv("XMVE_F64_BK");
     if (bk != nullptr && atoi(bk) == 16)
       score_f64_mma_kernel<16, 3><<<grid, 128, DmCfg<16, 3>::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
-          a, nq, a_ld, b, nv, b_ld, k, alpha, out, out_ld);
+          a, nq, a_ld, b, nv, b_ld, k, alpha, w, fuse, out, out_ld);
     else
       score_f64_mma_kernel<32, 2><<<grid, 128, DmCfg<32, 2>::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
-          a, nq, a_ld, b, nv, b_ld, k, alpha, out, out_ld);
+          a, nq, a_ld, b, nv, b_ld, k, alpha, w, fuse, out, out_ld);
     return launch_status("score_f64_mma_kernel");
   }
+  if (fuse != 0) return fail(XMVE_ERR_ARG, "score_f64_fused: operand rows must be 16-byte aligned (even row strides)");
   score_f64_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, nq, a_ld, b, nv, b_ld, k, alpha, out,
                                                                        out_ld);
   return launch_status("score_f64_kernel");
+}
+}  // namespace
+}  // namespace xmve
+
+extern "C" int xmve_score_f64(const double* a, int64_t nq, int64_t a_ld, const double* b, int64_t nv, int64_t b_ld,
+                              int k, double alpha, double* out, int64_t out_ld, void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  return launch_score_f64(a, nq, a_ld, b, nv, b_ld, k, alpha, 1.0, 0, out, out_ld, stream);
+}
+
+extern "C" int xmve_score_f64_fused(const double* a, int64_t nq, int64_t a_ld, const double* b, int64_t nv,
+                                    int64_t b_ld, int k, double alpha, double w, int first, double* out,
+                                    int64_t out_ld, void* stream) {
+  using namespace xmve;
+  XMVE_DEVICE_OR_RETURN();
+  return launch_score_f64(a, nq, a_ld, b, nv, b_ld, k, alpha, w, first ? 1 : 2, out, out_ld, stream);
 }

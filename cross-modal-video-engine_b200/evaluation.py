@@ -42,6 +42,10 @@ def _out(t, was_numpy):
     return t.cpu().numpy() if was_numpy else t
 
 
+def _is_f64(x):
+    return (x.dtype == torch.float64) if torch.is_tensor(x) else (getattr(x, "dtype", None) == np.float64)
+
+
 def _dt(t):
     return N.F64 if t.dtype == torch.float64 else N.F32
 
@@ -59,8 +63,13 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
-def score_matrix(queries, corpus, alpha, norm_mode=N.NORM_PLAIN):
-    """``alpha * l2norm(queries) @ l2norm(corpus).T`` on the device, dtype of the inputs."""
+def score_matrix(queries, corpus, alpha, norm_mode=N.NORM_PLAIN, fuse_into=None, fuse_w=1.0):
+    """``alpha * l2norm(queries) @ l2norm(corpus).T`` on the device, dtype of the inputs.
+
+    ``fuse_into`` (float64 inputs with an even dim only; returns None otherwise and the caller composes): instead of
+    returning the matrix E, accumulate it into ``fuse_into`` in the kernel's epilogue -- ``fuse_into = fuse_w * E`` when
+    ``fuse_into`` is a fresh ``("first", tensor)``, ``fuse_into += fuse_w * E`` for ``("add", tensor)`` -- with every
+    product and sum rounded on its own, like ``xmve_fuse_accumulate`` on the stored matrix."""
     q, _ = _host_in(queries)
     v, _ = _host_in(corpus)
     if q.dtype != v.dtype:
@@ -71,13 +80,23 @@ def score_matrix(queries, corpus, alpha, norm_mode=N.NORM_PLAIN):
     st = N.stream_ptr()
     if nq == 0 or nv == 0:
         return torch.empty((nq, nv), dtype=q.dtype, device=q.device)
+    if fuse_into is not None and not (q.dtype == torch.float64 and d % 2 == 0 and nq and nv):
+        return None
     if q.dtype == torch.float64:
         qn = torch.empty((nq, d), dtype=torch.float64, device=q.device)
         vn = torch.empty((nv, d), dtype=torch.float64, device=q.device)
         N.call("xmve_normalize_f64", N.ptr(q), N.F64, nq, d, q.stride(0), N.ptr(qn), d, norm_mode, st)
         N.call("xmve_normalize_f64", N.ptr(v), N.F64, nv, d, v.stride(0), N.ptr(vn), d, norm_mode, st)
-        out = torch.empty((nq, nv), dtype=torch.float64, device=q.device)
         step = 1 << 21
+        if fuse_into is not None:
+            how, out = fuse_into
+            assert out.shape == (nq, nv) and out.dtype == torch.float64 and out.stride(1) == 1
+            for q0 in range(0, nq, step):
+                q1 = min(nq, q0 + step)
+                N.call("xmve_score_f64_fused", N.ptr(qn[q0:]), q1 - q0, d, N.ptr(vn), nv, d, d, float(alpha),
+                       float(fuse_w), 1 if how == "first" else 0, N.ptr(out[q0:]), out.stride(0), st)
+            return out
+        out = torch.empty((nq, nv), dtype=torch.float64, device=q.device)
         for q0 in range(0, nq, step):
             q1 = min(nq, q0 + step)
             N.call("xmve_score_f64", N.ptr(qn[q0:]), q1 - q0, d, N.ptr(vn), nv, d, d, float(alpha),
@@ -170,6 +189,17 @@ def fused_errors(video_spaces, caption_spaces, weights, mode='weighted-cosine'):
     was_numpy = not torch.is_tensor(caption_spaces[0])
     acc = None
     for s_i, (V, Q, w) in enumerate(zip(video_spaces, caption_spaces, weights)):
+        if mode == 'weighted-cosine':
+            # float64 inputs: w_s * E_s is accumulated in the epilogue of the score kernel (no [Nq, Nv] round trip)
+            nq_, nv_ = len(Q), len(V)
+            if acc is None and _is_f64(Q) and _is_f64(V):
+                acc = torch.empty((nq_, nv_), dtype=torch.float64, device=_dev())
+                if score_matrix(Q, V, -1.0, fuse_into=("first", acc), fuse_w=w) is not None:
+                    continue
+                acc = None
+            elif acc is not None and acc.dtype == torch.float64 and _is_f64(Q) and _is_f64(V) \
+                    and score_matrix(Q, V, -1.0, fuse_into=("add", acc), fuse_w=w) is not None:
+                continue
         e = score_matrix(Q, V, -1.0)
         if mode == 'norm_score':
             e = norm_score(e)

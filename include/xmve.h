@@ -213,6 +213,14 @@ XMVE_API int xmve_normalize_f64(const void* src, int src_dtype, int64_t n, int d
                        double* dst, int64_t dst_ld, int norm_mode, void* stream);
 XMVE_API int xmve_score_f64(const double* a, int64_t nq, int64_t a_ld, const double* b, int64_t nv, int64_t b_ld,
                    int k, double alpha, double* out, int64_t out_ld, void* stream);
+/* The same with the multi-space fusion in the epilogue:
+ *   first != 0: out = w * (alpha * <a_q, b_v>);   first == 0: out = out + w * (alpha * <a_q, b_v>)
+ * every product and sum rounded on its own, i.e. exactly `acc = w * e` / `acc = acc + w * e` of NumPy on the matrix
+ * xmve_score_f64 would have written -- without writing and re-reading that matrix.  Needs even row strides and
+ * 16-byte aligned operands (the DMMA kernel); XMVE_ERR_ARG otherwise.
+ */
+XMVE_API int xmve_score_f64_fused(const double* a, int64_t nq, int64_t a_ld, const double* b, int64_t nv, int64_t b_ld,
+                         int k, double alpha, double w, int first, double* out, int64_t out_ld, void* stream);
 
 /* ---- non-cosine measures of cal_error (LINAS-engine/evaluation.py:22-35; scipy cdist / loss.jaccard_sim) -------
  * out[q, v] = alpha * f(a_q, b_v) + beta,  f = sum_i |a_i - b_i| (L1), sqrt(sum_i (a_i - b_i)^2) (L2) or

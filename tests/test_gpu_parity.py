@@ -99,6 +99,13 @@ def test_fused_errors_matrix(X, mode):
         X.native.call("xmve_fuse_accumulate", X.native.ptr(acc), acc.stride(0), X.native.ptr(t), t.stride(0), X.native.F64,
                       t.shape[0], t.shape[1], float(ws), 1 if s_i == 0 else 0, X.native.stream_ptr())
     np.testing.assert_array_equal(acc.cpu().numpy(), w[0] * e[0] + w[1] * e[1])
+    # float64 inputs take the score kernel's FUSED epilogue (no stored per-space matrix): bit-identical to composing
+    # the stored matrices of the same kernel
+    if mode == "weighted-cosine":
+        Vs = [V[:, :96].astype(np.float64), V[:, 96:].astype(np.float64)]
+        Qs = [Q[:, :96].astype(np.float64), Q[:, 96:].astype(np.float64)]
+        stored = [X.evaluation.cal_error(v, q) for v, q in zip(Vs, Qs)]
+        np.testing.assert_array_equal(X.evaluation.fused_errors(Vs, Qs, w), w[0] * stored[0] + w[1] * stored[1])
     with pytest.raises(ValueError):
         X.evaluation.fused_errors([V], [Q], [1.0], "max")
 

@@ -964,7 +964,7 @@ def bench_c2(ctx, args, steps, warmup):
     def sp(x):
         return [x[:, :DIMS[0]], x[:, DIMS[0]:]]
     torch.cuda.synchronize()
-    f64_events, unhook = ctx.hook(lambda name, a: name == "xmve_score_f64")
+    f64_events, unhook = ctx.hook(lambda name, a: name in ("xmve_score_f64", "xmve_score_f64_fused"))
 
     def step_device():
         e = evaluation.fused_errors(sp(Vd), sp(Qd), WEIGHTS)
@@ -1029,7 +1029,8 @@ def bench_c2(ctx, args, steps, warmup):
                 "h2d_bytes_per_step": (nq + nvid) * sum(DIMS) * 8, "d2h_bytes_per_step": 12 * 8,
                 "note": "pageable host float64 arrays + id lists in (get_gt on the host inside the step), 2 x 6 metrics out"},
         "gpu_launches": launches,
-        "roofline": {"kernel": "score_f64_mma_kernel (DMMA m8n8k4, cp.async ring)", "bound": "tensor",
+        "roofline": {"kernel": "score_f64_mma_kernel (DMMA m8n8k4, cp.async ring, fused multi-space epilogue)",
+                     "bound": "tensor",
                      "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
                      "algorithmic_flops": flops,

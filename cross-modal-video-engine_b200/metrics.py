@@ -147,6 +147,13 @@ class RankResult:
                      self.tallies, self.hist)
         return self
 
+    def ap_vector(self, first_only=False, ap_k=0):
+        """AP of every query as a device tensor, WITHOUT touching the reductions of the last :meth:`reduce` (lets
+        ``cal_perf`` enqueue everything of both directions before the first device -> host read)."""
+        ap = torch.empty(self.n_query, dtype=torch.float64, device=self.ranks.device)
+        rank_metrics(self.ranks, self.off, self.n_query, self.n_mem, first_only, ap_k, self.max_gt, None, ap, None, None)
+        return ap
+
     def recall_medr_meanr(self):
         n_q = self.n_query
         c1, c5, c10, rsum = (int(v) for v in self.tallies.cpu().tolist())

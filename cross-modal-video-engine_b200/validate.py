@@ -38,13 +38,14 @@ def cal_perf(t2v_all_errors, v2t_gt, t2v_gt, tb_logger=None, model=None):
     x = t2v_all_errors if torch.is_tensor(t2v_all_errors) else torch.from_numpy(t2v_all_errors)
     x = x.to(dev, non_blocking=True)
 
-    # video retrieval
-    t2v = metrics.RankResult(x, t2v_gt)
-    (t2v_r1, t2v_r5, t2v_r10, t2v_medr, t2v_meanr) = t2v.recall_medr_meanr()
-    t2v_map_score = t2v.reduce(first_only=True).mean_ap()
+    # everything of both directions is enqueued before the first device -> host read: the host builds the
+    # ground-truth CSR of the second direction while the GPU ranks the first
+    t2v = metrics.RankResult(x, t2v_gt)                        # video retrieval: rows
+    t2v_ap = t2v.ap_vector(first_only=True)                    # t2v_map marks only the first ground truth (:72-73)
+    v2t = metrics.RankResult(x.t(), v2t_gt)                    # caption retrieval: columns
 
-    # caption retrieval
-    v2t = metrics.RankResult(x.t(), v2t_gt)
+    (t2v_r1, t2v_r5, t2v_r10, t2v_medr, t2v_meanr) = t2v.recall_medr_meanr()
+    t2v_map_score = np.mean(t2v_ap.cpu().numpy())
     (v2t_r1, v2t_r5, v2t_r10, v2t_medr, v2t_meanr) = v2t.recall_medr_meanr()
     v2t_map_score = v2t.mean_ap()
 

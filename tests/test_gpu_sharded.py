@@ -37,3 +37,24 @@ def test_sharded_search_over_nccl_equals_one_store():
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "sharded search on %d GPUs: OK" % ranks in out.stdout
     assert "MISMATCH" not in out.stdout
+
+
+def test_two_stores_on_two_devices_in_one_process():
+    """function attributes (opt-in shared memory) and the scheduler-counter symbol were cached per PROCESS,
+    so the first launch on a second GPU of the same process failed.  A store on cuda:1, used while cuda:0 is the
+    current device, must give the same lists as the store on cuda:0 -- alone and as two shards of one search."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    from cross_modal_video_engine_b200 import engine, synth
+    torch.cuda.set_device(0)
+    nv, d, nq, k = 90_000, 128, 300, 20
+    V, Q = synth.gaussian(81, nv, d), synth.gaussian(82, nq, d)
+    s0 = engine.CorpusStore(nv, (d,), device="cuda:0").add(torch.from_numpy(V))
+    s1 = engine.CorpusStore(nv, (d,), device="cuda:1").add(torch.from_numpy(V))       # cuda:0 stays current
+    a_s, a_i = s0.search(torch.from_numpy(Q), k)
+    b_s, b_i = s1.search(torch.from_numpy(Q), k)
+    assert b_i.device.index == 1
+    assert torch.equal(a_i.cpu(), b_i.cpu()) and torch.equal(a_s.cpu(), b_s.cpu())
+    gs = engine.GraphSearch(s1, nq, k)                                               # capture on the non-current device
+    g_s, g_i = gs(torch.from_numpy(Q).to("cuda:1"))
+    assert torch.equal(g_i.cpu(), a_i.cpu())

@@ -532,3 +532,22 @@ def test_deep_lists_over_two_shards(X):
     one = X.engine.CorpusStore(nv, (d,)).add(torch.from_numpy(V))
     s1, i1 = one.search(torch.from_numpy(Q), k)
     assert torch.equal(i1, i) and torch.equal(s1, s)
+
+
+# ---- C1 with embeddings produced by the reference's random-init model ---------------------------------------------
+def test_c1_random_init_model_embeddings(X):
+    """BASELINE config 1 ("random-init model"): the embeddings come from the reference's own encoders
+    (oracle/make_golden_c1_model.py), the metrics / ranks / top-10 from the reference's evaluation on them."""
+    from test_oracle_golden import c1_model_inputs
+    g, vid, cap, video_ids, caption_ids = c1_model_inputs()
+    V64, Q64 = vid.astype(np.float64), cap.astype(np.float64)
+    errors = X.evaluation.cal_error(V64, Q64)
+    np.testing.assert_allclose(errors[:6, :6], g["errors_head"], rtol=0, atol=1e-14)
+    v2t_gt, t2v_gt = X.metrics.get_gt(video_ids, caption_ids)
+    np.testing.assert_array_equal(np.array(X.validate.cal_perf(errors, v2t_gt, t2v_gt), dtype=np.float64), g["perf"])
+    store = X.engine.CorpusStore(len(vid), (1536,)).add(torch.from_numpy(vid))
+    s, i = store.search(torch.from_numpy(cap), 10)
+    np.testing.assert_array_equal(i.cpu().numpy(), g["top10"])
+    res = X.metrics.RankResult.from_store(store, torch.from_numpy(cap), t2v_gt, first_only=True)
+    np.testing.assert_array_equal(res.ranks.cpu().numpy(), g["t2v_ranks"])
+    assert res.recall_medr_meanr() == tuple(g["perf"][1][:5])

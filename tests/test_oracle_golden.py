@@ -126,3 +126,26 @@ def test_multifusion_oracle_matches_reference_inference(name):
     tar_list = ["vid_%d.mp4" % int(x) for x in names]
     got = [multifusion.top1_name(torch.from_numpy(P[i:i + 1]), pooled, tar_list) for i in range(3)]
     assert got == rec["top1"]
+
+
+# ---- C1 with embeddings from the reference's random-init model (oracle/make_golden_c1_model.py) ------------------
+def c1_model_inputs():
+    g = load_golden("c1_model")
+    vid, cap = g["vid"], g["cap"]
+    n_v, per = len(vid), len(cap) // len(vid)
+    video_ids = ["video%d" % i for i in range(n_v)]
+    caption_ids = ["video%d#enc#%d" % (j // per, j % per) for j in range(len(cap))]
+    return g, vid, cap, video_ids, caption_ids
+
+
+def test_c1_random_init_model_embeddings_oracle():
+    g, vid, cap, video_ids, caption_ids = c1_model_inputs()
+    assert vid.dtype == np.float32 and vid.shape[1] == 1536
+    np.testing.assert_allclose(np.linalg.norm(vid.astype(np.float64), axis=1), 1.0, atol=1e-6)   # Latent_mapping l2norm
+    errors = linas.cal_error(vid.astype(np.float64), cap.astype(np.float64))
+    np.testing.assert_array_equal(errors[:6, :6], g["errors_head"])
+    assert errors.sum() == g["errors_sum"]
+    v2t_gt, t2v_gt = linas.get_gt(video_ids, caption_ids)
+    np.testing.assert_array_equal(np.array(linas.cal_perf(errors, v2t_gt, t2v_gt), dtype=np.float64), g["perf"])
+    np.testing.assert_array_equal(linas.gt_ranks(errors, t2v_gt), g["t2v_ranks"])
+    np.testing.assert_array_equal(np.stack([linas.topk_ids(errors[i], 10) for i in range(len(cap))]), g["top10"])

@@ -382,9 +382,12 @@ def peaks():
 def ncu_traffic(nv_local):
     """DRAM bytes per FILTER launch from the committed ncu --set full capture of this configuration (or None)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            t = json.load(f)
-        rec = t.get(str(int(nv_local)))
+        rec = None
+        for name in ("r2_traffic.json", "r1_traffic.json"):          # the latest capture that has this shard size
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                rec = json.load(f).get(str(int(nv_local)))
+            if rec:
+                break
         return (rec["bytes"], rec["source"]) if rec else (None, None)
     except Exception:
         return None, None

@@ -29,10 +29,16 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// gridDim.y blocks per query row (more when there are few rows); their warps walk the row's candidate slots.
+// gridDim.y blocks per query row (more when there are few rows) share the row's candidate slots evenly.  A block
+// works through its slots 1024 at a time in two phases: (A) all threads read the approximate scores, mark what is below
+// the bound and COMPACT the slots that need an exact score into a shared-memory list (one shared-memory add per warp
+// and 32 slots); (B) the warps take list entries round-robin, one warp-wide dot product each.  Without the list a
+// warp owned 32 fixed slots and the rows to rescore -- one slot in ten, Poisson-distributed -- left some warps with
+// twice the work of others; with 60 query rows (AVS) that imbalance was the kernel's duration.
 // The query row is widened to fp64 ONCE into shared memory: the inner loop then costs one F2F (corpus element) and
 // one DFMA per element -- the fp32->fp64 conversions, not HBM, were what bounded the first version (86 F2F vs 60 DFMA
 // in its SASS, 3.2 TB/s of gather); four 16-byte loads per lane are kept in flight.
+constexpr int RS_CHUNK = 1024;
 __global__ void __launch_bounds__(RS_WARPS * 32)
 rescore_kernel(const float* __restrict__ q_raw, int64_t nq, int64_t q_ld, const double* __restrict__ q_norm,
                const float* __restrict__ v_raw, int64_t nv, int64_t v_ld, const double* __restrict__ v_norm,
@@ -40,30 +46,43 @@ rescore_kernel(const float* __restrict__ q_raw, int64_t nq, int64_t q_ld, const 
                const int32_t* __restrict__ cand_idx, const int32_t* __restrict__ cand_count, int cap,
                const float* __restrict__ bound, const float* __restrict__ bound_hi, double* __restrict__ exact) {
   extern __shared__ __align__(16) double q_s[];
+  __shared__ int todo_list[RS_CHUNK];
+  __shared__ int todo_n;
   const int64_t q = blockIdx.x;
   const int dtot = sp.off[sp.n_space];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = min(cand_count[q], cap);
-  if (static_cast<int>(blockIdx.y) * RS_WARPS * 32 >= n) return;   // nothing for this block (uniform: before any barrier)
+  // this block's share of the slots, in whole groups of 32
+  const int per = ((n + 31) / 32 + static_cast<int>(gridDim.y) - 1) / static_cast<int>(gridDim.y) * 32;
+  const int s0 = static_cast<int>(blockIdx.y) * per, s1 = min(n, s0 + per);
+  if (s0 >= n) return;                                             // nothing for this block (uniform: before any barrier)
   for (int i = threadIdx.x; i < dtot; i += blockDim.x) q_s[i] = static_cast<double>(q_raw[q * q_ld + i]);
-  __syncthreads();
   const float bnd = bound ? bound[q] : -CUDART_INF_F;
   // second round: slots at or above bound_hi hold the exact scores of the first round and are left alone
   const float bnd_hi = bound_hi ? bound_hi[q] : CUDART_INF_F;
   const bool vec = (v_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(v_raw) & 15u) == 0);
-  // Each warp takes 32 candidate slots at a time: one coalesced read of their approximate scores and rows, a ballot
-  // of the ones that reach the bound (about one in ten), then one warp-wide dot product per survivor.
-  for (int base = (blockIdx.y * RS_WARPS + warp) * 32; base < n; base += gridDim.y * RS_WARPS * 32) {
-    const int c = base + lane;                                   // slots >= n are never read downstream
-    const float approx = c < n ? cand_score[q * cap + c] : -CUDART_INF_F;
-    const bool mine = c < n && approx >= bnd && approx < bnd_hi;
-    const int64_t my_v = mine ? cand_idx[q * cap + c] : 0;
-    if (c < n && approx < bnd) exact[q * cap + c] = -CUDART_INF;
-    unsigned todo = __ballot_sync(0xffffffffu, mine);
-    while (todo != 0) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int64_t v = __shfl_sync(0xffffffffu, my_v, src);
+  for (int c0 = s0; c0 < s1; c0 += RS_CHUNK) {
+    if (threadIdx.x == 0) todo_n = 0;
+    __syncthreads();                                               // (also: q_s is complete)
+    const int c1 = min(s1, c0 + RS_CHUNK);
+    for (int base = c0 + warp * 32; base < c1; base += RS_WARPS * 32) {
+      const int c = base + lane;                                   // slots >= n are never read downstream
+      const float approx = c < c1 ? cand_score[q * cap + c] : -CUDART_INF_F;
+      const bool mine = c < c1 && approx >= bnd && approx < bnd_hi;
+      if (c < c1 && approx < bnd) exact[q * cap + c] = -CUDART_INF;
+      const unsigned m = __ballot_sync(0xffffffffu, mine);
+      if (m != 0) {
+        int pos = 0;
+        if (lane == 0) pos = atomicAdd(&todo_n, __popc(m));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (mine) todo_list[pos + __popc(m & ((1u << lane) - 1u))] = c;
+      }
+    }
+    __syncthreads();
+    const int n_todo = todo_n;
+    for (int e = warp; e < n_todo; e += RS_WARPS) {
+      const int slot = todo_list[e];
+      const int64_t v = cand_idx[q * cap + slot];
       const float* __restrict__ vr = v_raw + v * v_ld;
       double res = 0.0;
       for (int s = 0; s < sp.n_space; ++s) {
@@ -121,8 +140,9 @@ rescore_kernel(const float* __restrict__ q_raw, int64_t nq, int64_t q_ld, const 
         }
         res += sp.w[s] * (acc / (nqv * nvv));
       }
-      if (lane == 0) exact[q * cap + base + src] = res;
+      if (lane == 0) exact[q * cap + slot] = res;
     }
+    __syncthreads();                                               // the list is reused by the next chunk
   }
 }
 
@@ -511,7 +531,8 @@ extern "C" int xmve_rescore(const float* q_raw, int64_t nq, int64_t q_ld, const 
   if (dtot > 6000) return fail(XMVE_ERR_LIMIT, "rescore: total raw dim %d > 6000 (48 KB of shared memory)", dtot);
   if (nq == 0) return XMVE_OK;
   // few query rows (AVS: 60): split every row's candidates over several blocks so that all SMs gather
-  int64_t split = (4 * 148 + nq - 1) / nq;
+  // (blocks whose share of the row's actual candidate count is empty leave at once)
+  int64_t split = (6 * 148 + nq - 1) / nq;
   if (split > 64) split = 64;
   if (split > (cap + RS_WARPS * 32 - 1) / (RS_WARPS * 32)) split = (cap + RS_WARPS * 32 - 1) / (RS_WARPS * 32);
   if (split < 1) split = 1;

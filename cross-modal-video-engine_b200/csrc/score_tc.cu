@@ -74,7 +74,8 @@ struct Cfg {
   static constexpr int EPI_COLS = NB == 2 ? BN : BN / 2;       // columns of a slot drained by one epilogue warp:
                                                                // wide: 4 warps per sub-tile; else two warps per
                                                                // TMEM lane quarter split the slot's 256 columns
-  static constexpr int PARK_BYTES = (THREADS - 128) * 8 * 8;   // STG (score, index) pairs per epilogue thread
+  static constexpr int PARK_BYTES = (THREADS - 128) * 2 * 8 * 8;   // two lists of STG (score, index) pairs per
+                                                                   // epilogue thread (see flush_parked)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + PARK_BYTES;
   static constexpr int TILE_M = BM * CTAS;                     // query rows per tile
   static constexpr int TILE_N = BN * NB;                       // corpus rows per tile
@@ -100,6 +101,8 @@ struct Params {
   float* cand_score;
   int32_t* cand_idx;
   int32_t cap;
+  int defer_append;                 // FILTER: finish a tile's append one tile later (default; XMVE_DEFER=0 disables)
+  int single_hit;                   // FILTER: branch-free extraction of a chunk's only candidate (XMVE_SINGLE_HIT=0 disables)
 };
 
 struct Unit {
@@ -136,10 +139,15 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 // appended to the row's global list AFTER the slot has been handed back to the MMA warp: one atomicAdd per
 // thread and tile, issued by all lanes of the warp together, instead of one blocking atomic per candidate
 // inside the divergent scan (which cost 25 % of the kernel at ~1e-3 candidates per score; profiles/).
-constexpr int STG = 8;                                   // parked candidates per thread
-__device__ __noinline__ void flush_parked(int32_t* cand_count, float* cand_score, int32_t* cand_idx, int cap,
-                                          int64_t row, const uint2* stg, int n) {
-  const int base = atomicAdd(&cand_count[row], n);
+//
+// The append is finished ONE TILE LATE: the atomicAdd that reserves the slots is issued right after the tile's
+// scan, but its result is first needed when the parked pairs are stored -- after the NEXT tile's scan (the
+// lists are double-buffered).  With the stores directly behind the atomic every epilogue warp sat out one L2
+// atomic round trip (~1.5 us) per tile, because almost every warp has some lane with a candidate: 3.5-4 us of
+// epilogue against 4.4 us of MMA per tile at K = 640 (profiles/r2_summary.md section 2).
+constexpr int STG = 8;                                   // parked candidates per thread and list
+__device__ __forceinline__ void store_parked(float* cand_score, int32_t* cand_idx, int cap, int64_t row, int base,
+                                             const uint2* stg, int n) {
   for (int e = 0; e < n; ++e) {
     const int slot = base + e;
     if (slot < cap) {
@@ -148,6 +156,12 @@ __device__ __noinline__ void flush_parked(int32_t* cand_count, float* cand_score
       cand_idx[row * cap + slot] = static_cast<int32_t>(c.y);
     }
   }
+}
+// the blocking form: a list that fills up in the middle of a scan (dense rows; rare)
+__device__ __noinline__ void flush_parked(int32_t* cand_count, float* cand_score, int32_t* cand_idx, int cap,
+                                          int64_t row, const uint2* stg, int n) {
+  const int base = atomicAdd(&cand_count[row], n);
+  store_parked(cand_score, cand_idx, cap, row, base, stg, n);
 }
 
 struct RowState {
@@ -181,6 +195,23 @@ __device__ __forceinline__ void filter_chunk(const Params& p, const uint32_t (&v
   const float a = max3(m[0], m[1], m[2]), b = max3(m[3], m[4], m[5]), c = max3(m[6], m[7], m[8]);
   if (max3(max3(a, b, c), m[9], m[10]) > st.lo) {
     const int64_t left = p.nv - col;                     // columns of this chunk inside the corpus
+    if (p.single_hit && left >= 32) {
+      // Only the lanes with a hit are here (the others wait at the reconvergence point), so what this costs is the
+      // length of THEIR instruction stream.  Almost always the chunk holds exactly ONE candidate: count the hits and
+      // take the position of the last one without a branch (three independent ALU operations per element) instead
+      // of walking eleven group tests, each a branch with its own reconvergence barrier.
+      int cnt = 0, pos = 0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const bool h = __uint_as_float(v[i]) > st.lo;
+        cnt += h ? 1 : 0;
+        pos = h ? i : pos;
+      }
+      if (cnt == 1) {                                    // the hit is the chunk's maximum
+        filter_one(p, st, max3(max3(a, b, c), m[9], m[10]), static_cast<int32_t>(col) + pos);
+        return;
+      }
+    }
     const int lim = left < 32 ? static_cast<int>(left) : 32;
 #pragma unroll
     for (int g = 0; g < 11; ++g) {
@@ -451,8 +482,13 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
     const int row_in_tile = static_cast<int>(rank) * BM + quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     RowState st;
-    st.stg = park + (threadIdx.x - EPI_WARP0 * 32) * STG;
+    uint2* const lists = park + (threadIdx.x - EPI_WARP0 * 32) * (2 * STG);
+    st.stg = lists;
     st.n = 0;
+    // the append of the previous tile that is still to be finished (its atomicAdd is in flight)
+    int pend_n = 0, pend_base = 0;
+    int64_t pend_row = 0;
+    const uint2* pend_stg = lists;
     int acc = 0;
     uint32_t acc_phase = 0;
     UnitFeed<DYN, PAIR> feed;
@@ -482,7 +518,17 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
         if (NB == 2) acc_phase ^= 1;
         else if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
         if (MODE == MODE_FILTER) {                             // the slot is already back with the MMA warp
-          if (st.n != 0) {
+          if (p.defer_append) {
+            if (pend_n != 0) store_parked(p.cand_score, p.cand_idx, p.cap, pend_row, pend_base, pend_stg, pend_n);
+            pend_n = st.n;
+            if (st.n != 0) {
+              pend_base = atomicAdd(&p.cand_count[st.row], st.n);   // first read a whole tile from now
+              pend_row = st.row;
+              pend_stg = st.stg;
+              st.stg = st.stg == lists ? lists + STG : lists;
+              st.n = 0;
+            }
+          } else if (st.n != 0) {
             flush_parked(p.cand_count, p.cand_score, p.cand_idx, p.cap, st.row, st.stg, st.n);
             st.n = 0;
           }
@@ -490,6 +536,8 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
         }
       }
     }
+    if (MODE == MODE_FILTER && pend_n != 0)
+      store_parked(p.cand_score, p.cand_idx, p.cap, pend_row, pend_base, pend_stg, pend_n);
   }
 
   ptx::tc_fence_before_sync();
@@ -736,5 +784,9 @@ extern "C" int xmve_score_filter(const void* a_op, int64_t nq, int64_t a_ld, con
   p.cand_score = cand_score;
   p.cand_idx = cand_idx;
   p.cap = cap;
+  p.defer_append = 1;
+  if (const char* env = getenv("XMVE_DEFER")) p.defer_append = atoi(env) != 0;
+  p.single_hit = 1;
+  if (const char* env = getenv("XMVE_SINGLE_HIT")) p.single_hit = atoi(env) != 0;
   return launch<MODE_FILTER>(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k, p, static_cast<cudaStream_t>(stream));
 }

@@ -340,7 +340,7 @@ struct Segments {
 };
 
 template <typename IdxT>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 select_topk_kernel(const double* __restrict__ score, const IdxT* __restrict__ idx, int64_t cols,
                    const int32_t* __restrict__ counts, int64_t idx_offset, const int64_t* __restrict__ exclude, int k,
                    const float* __restrict__ thr, float eps, const float* __restrict__ eps_dev,
@@ -380,8 +380,13 @@ select_topk_kernel(const double* __restrict__ score, const IdxT* __restrict__ id
     const IdxT id = idx ? idx[at(i)] : static_cast<IdxT>(i);          // idx == NULL: column number
     return (s > -CUDART_INF && !(exclude && static_cast<int64_t>(id) + idx_offset == excl)) ? s : -CUDART_INF;
   };
-  for (int64_t i = threadIdx.x; i < n_in; i += blockDim.x)
-    if (value(i) > -CUDART_INF) atomicAdd(&n_valid_s, 1);
+  {                                                                    // one shared-memory add per warp
+    int mine = 0;
+    for (int64_t i = threadIdx.x; i < n_in; i += blockDim.x) mine += value(i) > -CUDART_INF ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine != 0) atomicAdd(&n_valid_s, mine);
+  }
   __syncthreads();
   const int n_all = n_valid_s;                                         // every valid entry of the row
   // More valid entries than the sort holds (dense neighbourhoods: thousands of items within eps of the k-th
@@ -394,11 +399,16 @@ select_topk_kernel(const double* __restrict__ score, const IdxT* __restrict__ id
   __syncthreads();
   if (threadIdx.x == 0) n_valid_s = 0;
   __syncthreads();
-  for (int64_t i = threadIdx.x; i < n_in; i += blockDim.x) {
-    const double s = value(i);
-    if (s > -CUDART_INF && __double2float_rn(s) >= floor_f) {
-      const int pos = atomicAdd(&n_valid_s, 1);
-      if (pos < pmax) {
+  for (int64_t base = threadIdx.x & ~31; base < n_in; base += blockDim.x) {   // warp-aggregated compaction
+    const int64_t i = base + (threadIdx.x & 31);
+    const double s = i < n_in ? value(i) : -CUDART_INF;
+    const bool keep = s > -CUDART_INF && __double2float_rn(s) >= floor_f;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m != 0) {
+      int pos = 0;
+      if ((threadIdx.x & 31) == 0) pos = atomicAdd(&n_valid_s, __popc(m));
+      pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+      if (keep && pos < pmax) {
         keys[pos] = s;
         ids[pos] = idx ? idx[at(i)] : static_cast<IdxT>(i);
       }
@@ -471,7 +481,7 @@ int pow2_ceil(int64_t x) {
 // approximate score is below kth1 - eps cannot reach the top-k (exact <= approx + eps < kth1 <= true k-th).
 constexpr int PILOT_MAX = 1024;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 pilot_top_kernel(const double* __restrict__ exact, const int32_t* __restrict__ idx, const int32_t* __restrict__ counts,
                  int cap, int64_t idx_offset, const int64_t* __restrict__ exclude, int m, double* __restrict__ out) {
   __shared__ double buf[PILOT_MAX];
@@ -481,11 +491,16 @@ pilot_top_kernel(const double* __restrict__ exact, const int32_t* __restrict__ i
   const int64_t excl = exclude ? exclude[r] : -1;
   if (threadIdx.x == 0) n_s = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < n_in; i += blockDim.x) {
-    const double s = exact[r * cap + i];
-    if (s > -CUDART_INF && !(exclude && static_cast<int64_t>(idx[r * cap + i]) + idx_offset == excl)) {
-      const int pos = atomicAdd(&n_s, 1);
-      if (pos < PILOT_MAX) buf[pos] = s;          // more than PILOT_MAX (ties at the round-one bound): any subset is valid
+  for (int base = threadIdx.x & ~31; base < n_in; base += blockDim.x) {          // warp-aggregated compaction
+    const int i = base + (threadIdx.x & 31);
+    const double s = i < n_in ? exact[r * cap + i] : -CUDART_INF;
+    const bool keep = s > -CUDART_INF && !(exclude && static_cast<int64_t>(idx[r * cap + i]) + idx_offset == excl);
+    const unsigned mk = __ballot_sync(0xffffffffu, keep);
+    if (mk != 0) {
+      int pos = 0;
+      if ((threadIdx.x & 31) == 0) pos = atomicAdd(&n_s, __popc(mk));
+      pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(mk & ((1u << (threadIdx.x & 31)) - 1u));
+      if (keep && pos < PILOT_MAX) buf[pos] = s;  // more than PILOT_MAX (ties at the round-one bound): any subset is valid
     }
   }
   __syncthreads();
@@ -621,7 +636,9 @@ int launch_select(const double* score, const IdxT* idx, int64_t rows, int64_t co
     attr_bytes[dev] = smem_bytes;
   }
   // small sorts: 256 threads, so that eight rows are resident per SM (the kernel is a chain of short dependent phases)
-  const int threads = pmax <= 2048 ? 256 : 512;
+  // ... and a handful of rows (AVS: 60 queries): one block per row cannot fill the chip, so each block gets 1024
+  // threads and its sort phases are four times shorter
+  const int threads = pmax <= 2048 ? (rows <= 148 && pmax >= 1024 ? 1024 : 256) : (rows <= 296 ? 1024 : 512);
   select_topk_kernel<IdxT><<<static_cast<unsigned>(rows), threads, smem_bytes, st>>>(
       score, idx, cols, counts, idx_offset, exclude, k, thr, eps, eps_dev, bound, overflow, seg, pmax, out_score,
       out_idx, out_valid, cert, thr_next, n_uncertified);
@@ -710,7 +727,7 @@ extern "C" int xmve_pilot_top(const double* exact, const int32_t* idx, const int
   XMVE_REQUIRE(exact && idx && counts && out && rows >= 0 && cap > 0 && m > 0, "pilot_top: bad arguments");
   if (m > PILOT_MAX) return fail(XMVE_ERR_LIMIT, "pilot_top: m=%d exceeds %d", m, PILOT_MAX);
   if (rows == 0) return XMVE_OK;
-  pilot_top_kernel<<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  pilot_top_kernel<<<static_cast<unsigned>(rows), (rows <= 296 && m > 256) ? 1024 : 256, 0, static_cast<cudaStream_t>(stream)>>>(
       exact, idx, counts, cap, idx_offset, exclude, m, out);
   return launch_status("pilot_top_kernel");
 }

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -38,6 +39,12 @@ SMALL_NV = 16384
 #: measured at 24 % of the kernel (profiles/r2_filter_k640.md).
 THR_EPS_MARGIN = 0.0
 ROW_TOPJ_MAX = 4096
+#: size of the strided corpus sample that sets the per-query threshold: n / SAMPLE_DIV rows, clamped to
+#: [SAMPLE_MIN, SAMPLE_MAX] (plan()).  A larger sample costs a longer sampling pass and buys a tighter threshold,
+#: i.e. fewer candidates for the FILTER epilogue, the order statistics and the rescore.
+SAMPLE_DIV = int(os.environ.get("XMVE_SAMPLE_DIV", 128))
+SAMPLE_MIN = int(os.environ.get("XMVE_SAMPLE_MIN", 8192))
+SAMPLE_MAX = int(os.environ.get("XMVE_SAMPLE_MAX", 65536))
 _BM, _BN = 128, 256
 
 
@@ -320,7 +327,7 @@ class CorpusStore:
 def plan(k, n):
     """Sampling step, order statistics and candidate capacity for a top-``k`` search of ``n`` corpus rows."""
     n = int(n)
-    n_s = min(n, max(8192, min(65536, n // 128)))
+    n_s = min(n, max(SAMPLE_MIN, min(SAMPLE_MAX, n // SAMPLE_DIV)))
     step = max(1, n // max(n_s, 1))
     n_s = (n + step - 1) // step
     lam = k / step
@@ -571,11 +578,18 @@ class _Search:
             # very deep lists (k > 1000): one round against (kk-th largest approximate score over all shards) - 2 eps
             if self.solo:
                 bound = _row_kth(cands[0][1], cands[0][0], kk, 2.0, 0, eps_t)
-            else:
+            elif kk <= ROW_TOPJ_MAX:
                 tops = [_row_topj(c[1], c[0], kk) for c in cands]
                 if not tops:
                     tops = [torch.full((n_sub, kk), float("-inf"), dtype=torch.float32, device=dev)]
                 bound = _row_kth(_union(tops, comm), None, kk, 2.0, 0, eps_t)
+            else:
+                # deeper than xmve_row_topj extracts: the best shard's own kk-th largest approximate score is a lower
+                # bound on the kk-th largest of the union (looser, so a few more rows are rescored)
+                bound = torch.full((n_sub,), float("-inf"), dtype=torch.float32, device=dev)
+                for c in cands:
+                    bound = torch.maximum(bound, _row_kth(c[1], c[0], kk, 2.0, 0, eps_t))
+                bound = comm.max_(bound)
             ph.mark("bound")
             exacts = [s._rescore(q_sub, qn_sub, n_sub, self.wts, c, bound) for s, c in zip(self.live, cands)]
         ph.mark("rescore")
@@ -873,6 +887,15 @@ def _search_shards(stores, queries, k, weights, exclude, eps, small_nv, stats, c
             floor = torch.full_like(floor, float("-inf"))     # a complete list needs no floor
     if solo:
         thr = _row_kth(lists[0][0], lists[0][1], pl["j"], THR_EPS_MARGIN, j_cap, eps_t)
+    elif big_j > ROW_TOPJ_MAX:
+        # more order statistics than xmve_row_topj extracts (k in the thousands over a small corpus): the j-th largest
+        # of ONE shard's sample is a lower bound on the j-th largest of the union -- a valid, lower threshold; lists
+        # that overflow because of it go through the re-run path
+        thr = torch.full((nq,), float("-inf"), dtype=torch.float32, device=dev)
+        for sc, cnt in lists:
+            thr = torch.maximum(thr, _row_kth(sc, cnt, pl["j"], THR_EPS_MARGIN, 0, eps_t))
+        thr = comm.max_(thr)
+        floor = -comm.max_(-floor)
     else:
         tops = [_row_topj(sc, cnt, big_j) for sc, cnt in lists]
         if not tops:

@@ -90,6 +90,15 @@ def _pipeline_worker(rank, world, port, out_dir):
     ref = [cpu_model._sorted_topk(exact[r], torch.arange(nv), k, int(excl[r])) for r in range(nq)]
     ok = all(torch.equal(i[r], ref[r][1]) and torch.allclose(s[r], ref[r][0], rtol=0, atol=1e-12) for r in range(nq))
     ok = ok and stats.get("reruns", 0) >= 1                  # the re-run loop did run, identically on both ranks
+    # lists deeper than xmve_row_topj extracts (k = 8000 of 20 000 rows: j > 4096 and kk > 4096): the per-shard order
+    # statistics + all-reduce(max) stand in for the gathered ones
+    nv3, k3 = 20000, 8000
+    lo3, hi3 = distributed.shard_range(nv3, world, rank)
+    shard3 = cpu_model.ModelShard(V[lo3:hi3], (d,), index_offset=lo3)
+    assert engine.plan(k3, nv3)["j"] > engine.ROW_TOPJ_MAX
+    s3, i3 = engine.search_shards([shard3], Q[:3], k3, comm=distributed.GroupComm(), n_total=nv3, small_nv=1000)
+    ref3 = [cpu_model._sorted_topk(exact[r, :nv3], torch.arange(nv3), k3) for r in range(3)]
+    ok = ok and all(torch.equal(i3[r], ref3[r][1]) for r in range(3))
     # small-corpus branch across ranks
     s2, i2 = engine.search_shards([shard], Q, 5, comm=distributed.GroupComm(), n_total=nv, small_nv=10 ** 9)
     ref2 = [cpu_model._sorted_topk(exact[r], torch.arange(nv), 5) for r in range(nq)]

@@ -517,10 +517,13 @@ def test_graph_search_replays_equal_the_eager_search(X):
     assert torch.equal(i3, i_ref3) and torch.equal(s3, s_ref3)
 
 
-def test_deep_lists_over_two_shards(X):
+@pytest.mark.parametrize("nv,k", [(22_000, 2000), (20_000, 8000)])
+def test_deep_lists_over_two_shards(X, nv, k):
     """k = 2000 over a 22 k-row corpus cut into two shards (the sharded path asked row_topj for more
-    than its 4096-value capacity and raised XMVE_ERR_LIMIT; lists deeper than 1000 take the one-round rescore)."""
-    nv, d, nq, k = 22_000, 96, 9, 2000
+    than its 4096-value capacity and raised XMVE_ERR_LIMIT; lists deeper than 1000 take the one-round rescore), and
+    k = 8000 of 20 k rows, where both the sampled threshold (j > 4096) and the rescore bound (k > 4096) come from
+    per-shard order statistics joined by a maximum instead of the gathered top-j lists."""
+    d, nq = 96, 9
     V, Q = X.synth.gaussian(71, nv, d), X.synth.gaussian(72, nq, d)
     cut = 10_001
     shards = [X.engine.CorpusStore(cut, (d,)).add(torch.from_numpy(V[:cut])),

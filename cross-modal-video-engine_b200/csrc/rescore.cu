@@ -39,7 +39,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // one DFMA per element -- the fp32->fp64 conversions, not HBM, were what bounded the first version (86 F2F vs 60 DFMA
 // in its SASS, 3.2 TB/s of gather); four 16-byte loads per lane are kept in flight.
 constexpr int RS_CHUNK = 1024;
-__global__ void __launch_bounds__(RS_WARPS * 32)
+__global__ void __launch_bounds__(RS_WARPS * 32, 6)
 rescore_kernel(const float* __restrict__ q_raw, int64_t nq, int64_t q_ld, const double* __restrict__ q_norm,
                const float* __restrict__ v_raw, int64_t nv, int64_t v_ld, const double* __restrict__ v_norm,
                const __grid_constant__ SpaceDesc sp, int norm_mode, const float* __restrict__ cand_score,
@@ -531,14 +531,27 @@ extern "C" int xmve_rescore(const float* q_raw, int64_t nq, int64_t q_ld, const 
   if (dtot > 6000) return fail(XMVE_ERR_LIMIT, "rescore: total raw dim %d > 6000 (48 KB of shared memory)", dtot);
   if (nq == 0) return XMVE_OK;
   // few query rows (AVS: 60): split every row's candidates over several blocks so that all SMs gather
-  // (blocks whose share of the row's actual candidate count is empty leave at once)
-  int64_t split = (6 * 148 + nq - 1) / nq;
+  // (blocks whose share of the row's actual candidate count is empty leave at once).  The grid is kept within ONE
+  // wave of resident blocks: 900 blocks on 740 slots ran as 1.2 waves, i.e. at 60 % of the gather bandwidth.
+  const size_t dyn_smem = dtot * sizeof(double);
+  static int resident[MAX_DEVICES][2] = {};                         // per device: [dynamic bytes it was queried for, blocks]
+  const int dev = current_device();
+  if (dev < 0) return fail(XMVE_ERR_DEVICE, "rescore: no current device");
+  if (resident[dev][1] == 0 || resident[dev][0] != static_cast<int>(dyn_smem)) {
+    int per_sm = 0;
+    XMVE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rescore_kernel, RS_WARPS * 32, dyn_smem));
+    const int sms = sm_count();
+    if (per_sm <= 0 || sms <= 0) return fail(XMVE_ERR_DEVICE, "rescore: cannot query the occupancy");
+    resident[dev][0] = static_cast<int>(dyn_smem);
+    resident[dev][1] = per_sm * sms;
+  }
+  int64_t split = resident[dev][1] / nq;
   if (split > 64) split = 64;
   if (split > (cap + RS_WARPS * 32 - 1) / (RS_WARPS * 32)) split = (cap + RS_WARPS * 32 - 1) / (RS_WARPS * 32);
   if (split < 1) split = 1;
   if (nq > 2147483647) return fail(XMVE_ERR_LIMIT, "rescore: too many query rows");
   const dim3 grid(static_cast<unsigned>(nq), static_cast<unsigned>(split));
-  rescore_kernel<<<grid, RS_WARPS * 32, dtot * sizeof(double), static_cast<cudaStream_t>(stream)>>>(
+  rescore_kernel<<<grid, RS_WARPS * 32, dyn_smem, static_cast<cudaStream_t>(stream)>>>(
       q_raw, nq, q_ld, q_norm, v_raw, nv, v_ld, v_norm, sp, norm_mode, cand_score, cand_idx, cand_count, cap, bound,
       bound_hi, exact);
   return launch_status("rescore_kernel");

@@ -227,38 +227,57 @@ __device__ __forceinline__ void filter_chunk(const Params& p, const uint32_t (&v
   }
 }
 
-__device__ __forceinline__ void store_chunk(const Params& p, const uint32_t (&v)[32], int64_t row, int64_t col) {
-  if (row >= p.nq) return;
-  float* dst = p.out + row * p.out_ld + col;
-  if (p.vec_ok && col + 32 <= p.nv) {
+// STORE: 32 rows x 32 columns held one row per lane (the TMEM load layout) go through a 4 KB per-warp shared-memory
+// tile so that every global store instruction writes whole 128-byte row segments (a quarter-warp per row) instead of
+// 32 scattered 16-byte pieces, one per row: with the direct form the LSU, not the MMA, set the pace of the STORE
+// kernels at K = 640 (profiles/r2_summary.md section 7).  16-byte slots are XOR-swizzled by the row so that both the
+// row-wise writes and the transposed reads are conflict-free.  All 32 lanes call it; `row0` is lane 0's row.
+__device__ __forceinline__ void store_chunk(const Params& p, const uint32_t (&v)[32], int64_t row0, int64_t col,
+                                            float4* wbuf, int lane) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      float4 w = make_float4(p.alpha * __uint_as_float(v[i]), p.alpha * __uint_as_float(v[i + 1]),
-                             p.alpha * __uint_as_float(v[i + 2]), p.alpha * __uint_as_float(v[i + 3]));
-      *reinterpret_cast<float4*>(dst + i) = w;
+  for (int j = 0; j < 8; ++j)
+    wbuf[lane * 8 + (j ^ (lane & 7))] =
+        make_float4(p.alpha * __uint_as_float(v[4 * j]), p.alpha * __uint_as_float(v[4 * j + 1]),
+                    p.alpha * __uint_as_float(v[4 * j + 2]), p.alpha * __uint_as_float(v[4 * j + 3]));
+  __syncwarp();
+  const int jj = lane & 7;
+  const int64_t c = col + 4 * jj;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + (lane >> 3);
+    const float4 x = wbuf[r * 8 + (jj ^ (r & 7))];
+    const int64_t row = row0 + r;
+    if (row < p.nq) {
+      float* dst = p.out + row * p.out_ld + c;
+      if (p.vec_ok && c + 3 < p.nv) {
+        *reinterpret_cast<float4*>(dst) = x;
+      } else {
+        if (c < p.nv) dst[0] = x.x;
+        if (c + 1 < p.nv) dst[1] = x.y;
+        if (c + 2 < p.nv) dst[2] = x.z;
+        if (c + 3 < p.nv) dst[3] = x.w;
+      }
     }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (col + i < p.nv) dst[i] = p.alpha * __uint_as_float(v[i]);
   }
+  __syncwarp();                                          // the tile is rewritten by the next chunk
 }
 
 // COLS columns of one 128-row accumulator slot -> STORE or FILTER (this thread owns query row st.row).  The TMEM
 // loads are software-pipelined: chunk c+1 is in flight while chunk c is examined.
 template <int MODE, int COLS>
 __device__ __forceinline__ void epilogue_slot(const Params& p, uint32_t taddr, RowState& st, int64_t col0) {
+  const int lane = threadIdx.x & 31;
   uint32_t v0[32], v1[32];
   ptx::tmem_ld_32x32(taddr, v0);
 #pragma unroll 1
   for (int c = 0; c < COLS / 32; c += 2) {
     ptx::tmem_ld_wait();
     ptx::tmem_ld_32x32(taddr + (c + 1) * 32, v1);
-    if (MODE == MODE_STORE) store_chunk(p, v0, st.row, col0 + c * 32);
+    if (MODE == MODE_STORE) store_chunk(p, v0, st.row - lane, col0 + c * 32, reinterpret_cast<float4*>(st.stg - lane * 2 * STG), lane);
     else filter_chunk(p, v0, st, col0 + c * 32);
     ptx::tmem_ld_wait();
     if (c + 2 < COLS / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, v0);
-    if (MODE == MODE_STORE) store_chunk(p, v1, st.row, col0 + (c + 1) * 32);
+    if (MODE == MODE_STORE) store_chunk(p, v1, st.row - lane, col0 + (c + 1) * 32, reinterpret_cast<float4*>(st.stg - lane * 2 * STG), lane);
     else filter_chunk(p, v1, st, col0 + (c + 1) * 32);
   }
 }
@@ -724,18 +743,19 @@ int launch_cfg(const void* a_op, int64_t nq, int64_t a_ld, const void* b_op, int
   return launch_status(!PAIR ? "score_kernel" : (NB == 2 ? "score_wide_kernel" : "score_pair_kernel"));
 }
 
-// Tile choice (measured, profiles/r1_tile_schedule_sweep.md).  The kernel runs at the 1 kW power cap, so operand
-// bytes moved per flop decide the sustained rate.  The CTA-pair tile moves a third less than the single-CTA tile
-// and, with the DYNAMIC unit scheduler, reads every corpus line from DRAM once (16.4 GB for an 8.2 GB operand and
-// two query super-blocks; with the static assignment the workers sharing a corpus tile drifted apart and the pair
-// kernels re-read it ~10x): +5 % over the single-CTA tile at realistic candidate densities.  The wide tile moves
-// the fewest bytes but cannot overlap its epilogue; it wins only where nothing is appended (STORE) and both
-// operands are L2-resident.
+// Tile choice (measured, profiles/r1_tile_schedule_sweep.md, profiles/r2_summary.md section 7).  The kernel runs at
+// the 1 kW power cap, so operand bytes moved per flop decide the sustained rate.  The CTA-pair tile moves a third
+// less than the single-CTA tile and, with the DYNAMIC unit scheduler, reads every corpus line from DRAM once (16.4 GB
+// for an 8.2 GB operand and two query super-blocks; with the static assignment the workers sharing a corpus tile
+// drifted apart and the pair kernels re-read it ~10x): +5 % over the single-CTA tile at realistic candidate
+// densities.  The wide tile moves the fewest bytes but cannot overlap its epilogue: since the STORE epilogue writes
+// coalesced row segments the pair tile beats it on every STORE shape measured (sampling passes, the 59 800 x 2 990
+// evaluation), with the static assignment while both operands stay in L2.
 template <int MODE>
 int launch(const void* a_op, int64_t nq, int64_t a_ld, const void* b_op, int64_t nv, int64_t b_ld, int64_t b_row_step,
            int k, Params p, cudaStream_t stream) {
   const int64_t operand_bytes = (nq + nv) * static_cast<int64_t>(k) * 2;
-  int tile = (MODE == MODE_STORE && operand_bytes <= (int64_t(48) << 20) && k >= 512) ? 2 : 4;
+  int tile = (MODE == MODE_STORE && operand_bytes <= (int64_t(48) << 20)) ? 1 : 4;
   if (nq <= BM) tile = 5;   // a handful of queries (AVS, online search): HBM-bound, half of a 256-row query tile is padding
   if (const char* env = getenv("XMVE_TILE")) tile = atoi(env);
   if (tile == 2) return launch_cfg<MODE, true, 2>(a_op, nq, a_ld, b_op, nv, b_ld, b_row_step, k, p, stream);

@@ -30,14 +30,27 @@ from . import _native as N
 #: (search(eps=...) callers, NaN rows); the search itself uses :func:`measured_eps` (typically 3.5e-3 - 4e-3).
 EPS_X1 = 8.5e-3
 SMALL_NV = 16384
-#: multiples of eps subtracted from the sampled threshold kth(sample, j).  Round 1 used 2: "the k-th best exact score
-#: is at least kth_approx - eps, a row's approximate score at most eps above its exact one".  But j already carries a
-#: 5.5-sigma sampling slack (plan()): the j-th largest of the sample sits near corpus rank j * step (1 500 at C5), an
-#: order of magnitude below the k-th best, so the certificate kth_exact - eps >= thr holds without the extra margin
-#: (P(miss) ~ 1e-7 per row; a miss only costs a re-run of that row).  Dropping it cuts the candidate lists from
-#: 5 800 to 1 500 per query at C5 and from 2 350 to 1 200 at C4, where the FILTER epilogue's candidate path was
-#: measured at 24 % of the kernel (profiles/r2_filter_k640.md).
+#: multiples of eps subtracted from the sampled threshold kth(sample, j) -- see :func:`thr_margin`.  Round 1 always
+#: used 2: "the k-th best exact score is at least kth_approx - eps, a row's approximate score at most eps above its
+#: exact one".  But j already carries a 5.5-sigma sampling slack (plan()): the j-th largest of the sample sits near
+#: corpus rank j * step (1 500 at C5), an order of magnitude below the k-th best, so the certificate
+#: kth_exact - eps >= thr holds without the extra margin (P(miss) ~ 1e-7 per row; a miss only costs a re-run of that
+#: row).  Dropping it cuts the candidate lists from 5 800 to 1 500 per query at C5 and from 2 350 to 1 200 at C4.
 THR_EPS_MARGIN = 0.0
+
+
+def thr_margin(lam):
+    """Multiples of eps to subtract from ``kth(sample, j)`` for ``lam = k / step`` expected top-k rows in the sample.
+
+    The margin-free threshold lives on the score gap between corpus rank ``k`` and rank ``j * step``.  The rank ratio
+    ``j / lam = 1 + 5.5 / sqrt(lam) + 4 / lam`` is >= 3.3 for ``lam <= 8.5`` (a gap of ~0.4 sigma of the score
+    distribution against eps ~ 0.2 sigma) but tends to 1 for deep lists over small corpora (k = 1000 of 200 k rows:
+    1.9), where the missing margin showed up as re-runs -- a whole extra FILTER pass for the rows concerned
+    (profiles/r2_summary.md section 6).  So: none up to lam = 8.5, one eps up to 64, the rigorous two beyond.  A wrong
+    guess costs time, never correctness (the certificate decides)."""
+    if lam <= 8.5:
+        return THR_EPS_MARGIN
+    return max(THR_EPS_MARGIN, 1.0 if lam <= 64.0 else 2.0)
 ROW_TOPJ_MAX = 4096
 #: size of the strided corpus sample that sets the per-query threshold: n / SAMPLE_DIV rows, clamped to
 #: [SAMPLE_MIN, SAMPLE_MAX] (plan()).  A larger sample costs a longer sampling pass and buys a tighter threshold,
@@ -335,7 +348,8 @@ def plan(k, n):
     cap = 1 << max(11, int(math.ceil(math.log2(8 * step * j))))
     cap = min(cap, 32768)
     j_cap = max(j, int(0.5 * cap / step))
-    return {"step": step, "n_sample": n_s, "j": min(j, n_s), "j_cap": min(j_cap, n_s), "cap": cap}
+    return {"step": step, "n_sample": n_s, "j": min(j, n_s), "j_cap": min(j_cap, n_s), "cap": cap,
+            "margin": thr_margin(lam)}
 
 
 def measured_eps(dq, dv, wts, n_space, k_len):
@@ -799,7 +813,7 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
        all-reduced once per corpus state, the query side is identical on every rank).
     2. the largest scores of a ``step``-strided sample of each shard (a coarse K2 STORE pass sets a floor, a K2
        FILTER pass over the sample keeps what exceeds it); the top-J of every shard are gathered and the global
-       threshold is ``max(kth(union, j) - THR_EPS_MARGIN * eps, kth(union, j_cap))`` -- what one GPU would compute on the whole
+       threshold is ``max(kth(union, j) - thr_margin(k / step) * eps, kth(union, j_cap))`` -- what one GPU would compute on the whole
        corpus, so each shard appends only its share of the candidates.
     3. K2 FILTER over each shard (the score matrix never reaches HBM).
     4. exact fp64 rescore in two rounds: every shard rescores its best ``m`` approximate candidates; the pilots are
@@ -886,14 +900,14 @@ def _search_shards(stores, queries, k, weights, exclude, eps, small_nv, stats, c
             lists.append((s._sample(a_op, nq, pl["step"]), None))
             floor = torch.full_like(floor, float("-inf"))     # a complete list needs no floor
     if solo:
-        thr = _row_kth(lists[0][0], lists[0][1], pl["j"], THR_EPS_MARGIN, j_cap, eps_t)
+        thr = _row_kth(lists[0][0], lists[0][1], pl["j"], pl["margin"], j_cap, eps_t)
     elif big_j > ROW_TOPJ_MAX:
         # more order statistics than xmve_row_topj extracts (k in the thousands over a small corpus): the j-th largest
         # of ONE shard's sample is a lower bound on the j-th largest of the union -- a valid, lower threshold; lists
         # that overflow because of it go through the re-run path
         thr = torch.full((nq,), float("-inf"), dtype=torch.float32, device=dev)
         for sc, cnt in lists:
-            thr = torch.maximum(thr, _row_kth(sc, cnt, pl["j"], THR_EPS_MARGIN, 0, eps_t))
+            thr = torch.maximum(thr, _row_kth(sc, cnt, pl["j"], pl["margin"], 0, eps_t))
         thr = comm.max_(thr)
         floor = -comm.max_(-floor)
     else:
@@ -905,7 +919,7 @@ def _search_shards(stores, queries, k, weights, exclude, eps, small_nv, stats, c
         per = u.shape[1] // comm.world
         floor = u.view(nq, comm.world, per)[:, :, -1].min(dim=1).values
         u.view(nq, comm.world, per)[:, :, -1] = float("-inf")
-        thr = _row_kth(u, None, pl["j"], THR_EPS_MARGIN, j_cap, eps_t)
+        thr = _row_kth(u, None, pl["j"], pl["margin"], j_cap, eps_t)
     # a two-level list that came out too short gives -inf (or a value below the floor): fall back to the coarse
     # floor, which ~0.4 % of the corpus exceeds -- far more than k rows, so it is below the k-th best score
     thr = torch.maximum(thr, floor - 2.0 * eps_t)

@@ -38,6 +38,19 @@ def test_plan_invariants(k, n):
     assert 1 <= p["j"] <= p["j_cap"] <= p["n_sample"]
     assert 2048 <= p["cap"] <= 32768
     assert p["j"] >= k / p["step"]                       # the order statistic sits above the expected k-th sample
+    lam = k / p["step"]
+    assert p["margin"] == engine.thr_margin(lam) and p["margin"] in (0.0, 1.0, 2.0)
+    # the eps margin may only be dropped while the rank ratio j / lam leaves a score gap of its own
+    assert p["margin"] > 0.0 or p["j"] / lam >= 3.3
+
+
+def test_benchmark_configs_search_without_the_margin():
+    """The BASELINE configs keep the margin-free threshold (their candidate counts and result digests are those of
+    the committed profiles); deep lists over small corpora get the margin back."""
+    for k, n in ((100, 10_000_000), (101, 1_000_000), (1000, 1_080_000), (100, 1_250_000)):
+        assert engine.plan(k, n)["margin"] == 0.0
+    assert engine.plan(1000, 200_000)["margin"] == 1.0
+    assert engine.plan(8000, 20_000)["margin"] == 2.0
 
 
 @settings(max_examples=100, deadline=None)

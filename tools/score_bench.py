@@ -57,6 +57,8 @@ def main():
     ap.add_argument("--thr", type=float, default=0.5)
     ap.add_argument("--cap", type=int, default=256)
     ap.add_argument("--sustain", type=float, default=0.0, help="seconds of back-to-back launches with clock sampling")
+    ap.add_argument("--store", action="store_true", help="time the STORE epilogue (fp32 score matrix written) instead")
+    ap.add_argument("--step", type=int, default=1, help="corpus row stride (the strided sample view)")
     ap.add_argument("--cublas", action="store_true", help="also time torch.matmul on (a chunk of) the same operands")
     args = ap.parse_args()
     N.require_device()
@@ -71,7 +73,8 @@ def main():
             out[r0:r1] = (x / x.norm(dim=1, keepdim=True)).to(torch.bfloat16)
         return out
 
-    a, b = unit(args.nq), unit(args.nv)
+    a, b = unit(args.nq), unit(args.nv * args.step)
+    out = torch.empty((args.nq, args.nv), dtype=torch.float32, device=dev) if args.store else None
     lo = torch.full((args.nq,), args.thr, device=dev)
     cap = args.cap
     cc = torch.zeros(args.nq, dtype=torch.int32, device=dev)
@@ -85,6 +88,10 @@ def main():
         os.environ["XMVE_TILE"] = str(tile)
 
         def run():
+            if args.store:
+                N.call("xmve_score_store", N.ptr(a), args.nq, a.stride(0), N.ptr(b), args.nv, b.stride(0), args.step, args.k,
+                       1.0, N.ptr(out), out.stride(0), N.stream_ptr())
+                return
             cc.zero_()
             N.call("xmve_score_filter", N.ptr(a), args.nq, a.stride(0), N.ptr(b), args.nv, b.stride(0), 1, args.k, N.ptr(lo),
                    None, None, N.ptr(cc), N.ptr(cs), N.ptr(ci), cap, N.stream_ptr())
@@ -98,6 +105,11 @@ def main():
             e1.record()
         torch.cuda.synchronize()
         ms = sorted(e0.elapsed_time(e1) for e0, e1 in ev)
+        if args.store:                                             # spot check against a matmul of the same operands
+            ref = a[:64].float() @ b[:: args.step][: args.nv].float().T
+            err = float((out[:64] - ref).abs().max())
+            print("store check: max |out - fp32 matmul| over 64 rows = %.2e" % err, flush=True)
+            assert err < 1e-4
         print("tile=%d nq=%d nv=%d k=%d  ms min/med/max %.3f %.3f %.3f  TFLOP/s(med) %.1f  cand_max %d" % (
             tile, args.nq, args.nv, args.k, ms[0], ms[len(ms) // 2], ms[-1], flops / ms[len(ms) // 2] / 1e9,
             int(cc.max())), flush=True)

@@ -1,6 +1,6 @@
 """Kernel timeline of ONE sharded search step on rank 0 (torch.profiler / CUPTI), under torchrun:
 
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/trace_step.py [nv] [nq] [k]
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/trace_step.py [nv] [nq] [k] [dim]
 
 Prints every GPU activity of the step in start order with its duration and the idle gap before it -- the tool
 behind the tail analysis of the multi-GPU step (where ncu cannot go: it must not wrap a multi-rank command)."""
@@ -19,6 +19,8 @@ def main():
     nq = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
     dims, w = (1536, 512), (0.6, 0.4)
     k = int(sys.argv[3]) if len(sys.argv) > 3 else 100
+    if len(sys.argv) > 4:                                   # one space of that many dims (C4: 640)
+        dims, w = (int(sys.argv[4]),), (1.0,)
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

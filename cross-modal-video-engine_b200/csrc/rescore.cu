@@ -46,7 +46,8 @@ rescore_kernel(const float* __restrict__ q_raw, int64_t nq, int64_t q_ld, const 
                const int32_t* __restrict__ cand_idx, const int32_t* __restrict__ cand_count, int cap,
                const float* __restrict__ bound, const float* __restrict__ bound_hi, double* __restrict__ exact) {
   extern __shared__ __align__(16) double q_s[];
-  __shared__ int todo_list[RS_CHUNK];
+  __shared__ int todo_list[RS_CHUNK];                                // slots that need an exact score ...
+  __shared__ int todo_row[RS_CHUNK];                                 // ... and their corpus rows
   __shared__ int todo_n;
   const int64_t q = blockIdx.x;
   const int dtot = sp.off[sp.n_space];
@@ -69,24 +70,34 @@ rescore_kernel(const float* __restrict__ q_raw, int64_t nq, int64_t q_ld, const 
       const int c = base + lane;                                   // slots >= n are never read downstream
       const float approx = c < c1 ? cand_score[q * cap + c] : -CUDART_INF_F;
       const bool mine = c < c1 && approx >= bnd && approx < bnd_hi;
+      const int row = mine ? cand_idx[q * cap + c] : 0;
       if (c < c1 && approx < bnd) exact[q * cap + c] = -CUDART_INF;
       const unsigned m = __ballot_sync(0xffffffffu, mine);
       if (m != 0) {
         int pos = 0;
         if (lane == 0) pos = atomicAdd(&todo_n, __popc(m));
-        pos = __shfl_sync(0xffffffffu, pos, 0);
-        if (mine) todo_list[pos + __popc(m & ((1u << lane) - 1u))] = c;
+        pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
+        if (mine) {
+          todo_list[pos] = c;
+          todo_row[pos] = row;
+        }
       }
     }
     __syncthreads();
     const int n_todo = todo_n;
+    // One warp-wide dot product per list entry; the row number comes from the list (read coalesced in phase A) and
+    // the row's norm is requested before the row, so the row data is the only dependent global load.  Variants
+    // measured and not kept (profiles/r2_summary.md section 8): two rows per warp (-11 % at D = 2048, +5 % at
+    // D = 640) and six or eight loads in flight per lane (+30 %: fewer resident warps, spilled registers).
     for (int e = warp; e < n_todo; e += RS_WARPS) {
       const int slot = todo_list[e];
-      const int64_t v = cand_idx[q * cap + slot];
+      const int64_t v = todo_row[e];
       const float* __restrict__ vr = v_raw + v * v_ld;
       double res = 0.0;
       for (int s = 0; s < sp.n_space; ++s) {
         const int lo = sp.off[s], hi = sp.off[s + 1];
+        double nvv = v_norm[static_cast<int64_t>(s) * nv + v];
+        double nqv = q_norm[static_cast<int64_t>(s) * nq + q];
         double acc = 0.0;
         if (vec && (lo % 4 == 0) && ((hi - lo) % 4 == 0)) {
           const float4* v4 = reinterpret_cast<const float4*>(vr + lo);
@@ -133,7 +144,6 @@ rescore_kernel(const float* __restrict__ q_raw, int64_t nq, int64_t q_ld, const 
           for (int i = lo + lane; i < hi; i += 32) acc = fma(q_s[i], static_cast<double>(vr[i]), acc);
         }
         acc = warp_sum(acc);
-        double nqv = q_norm[static_cast<int64_t>(s) * nq + q], nvv = v_norm[static_cast<int64_t>(s) * nv + v];
         if (norm_mode == XMVE_NORM_EPS) {
           nqv = fmax(nqv, 1e-12);
           nvv = fmax(nvv, 1e-12);

@@ -90,6 +90,20 @@ def test_score_store_matches_fp32_matmul_of_the_operands(N, nq, nv, d, tile, mon
     assert err < 2e-6, "tcgen05 tile mismatch: max abs err %g" % err      # fp32 accumulation of exact products
 
 
+@pytest.mark.parametrize("nv,pad", [(1000, 24), (333, 5), (70, 2)])
+def test_score_store_leaves_the_row_padding_alone(N, nv, pad):
+    """Rows of the output are written through 128-byte segments staged in shared memory: columns >= nv of a padded
+    output (out_ld > nv; aligned and unaligned leading dimensions) must keep the caller's bytes."""
+    nq, d = 300, 256
+    q, v, a, b = _operands(N, nq, nv, d, seed=11)
+    out = torch.full((nq, nv + pad), -7.0, dtype=torch.float32, device="cuda")
+    N.call("xmve_score_store", N.ptr(a), nq, a.stride(0), N.ptr(b), nv, b.stride(0), 1, a.shape[1], 1.0, N.ptr(out),
+           out.stride(0), N.stream_ptr())
+    ref = a[:nq].double() @ b[:nv].double().T
+    assert float((out[:, :nv].double() - ref).abs().max()) < 2e-6
+    assert bool((out[:, nv:] == -7.0).all())
+
+
 @pytest.mark.parametrize("tile", [6, 4, 1])
 def test_score_store_many_units_slow_epilogue(N, tile, monkeypatch):
     """20 000 x 2 990 x 4608 (the fp32 cal_error of the MSR-VTT shape): thousands of work units, many of them empty,
@@ -135,12 +149,16 @@ def test_score_store_strided_sample(N):
 
 
 @pytest.mark.parametrize("tile", [6, 5, 4, 2, 1, 0])
-@pytest.mark.parametrize("nq,nv,d,use_hi", [(300, 50000, 512, False), (77, 3000, 100, True), (1000, 200000, 128, False)])
-def test_score_filter_window(N, nq, nv, d, use_hi, tile, monkeypatch):
+@pytest.mark.parametrize("nq,nv,d,use_hi,quant", [(300, 50000, 512, False, 0.98), (77, 3000, 100, True, 0.98),
+                                                  (1000, 200000, 128, False, 0.98),
+                                                  # sparse windows: nearly every 32-column chunk that holds a candidate
+                                                  # holds exactly one (the branch-free extraction), some hold two
+                                                  (520, 60000, 640, False, 0.9985), (130, 40000, 192, True, 0.9985)])
+def test_score_filter_window(N, nq, nv, d, use_hi, quant, tile, monkeypatch):
     monkeypatch.setenv("XMVE_TILE", str(tile))
     q, v, a, b = _operands(N, nq, nv, d, seed=11)
     s = (a[:nq].float() @ b[:nv].float().T)
-    lo = torch.quantile(s[:, :2000], 0.98, dim=1).contiguous()
+    lo = torch.quantile(s[:, :2000], quant, dim=1).contiguous()
     hi = (lo + 0.05).contiguous() if use_hi else None
     cap = 8192
     cnt_above = torch.zeros(nq, dtype=torch.int32, device="cuda")

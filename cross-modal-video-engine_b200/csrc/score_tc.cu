@@ -116,12 +116,15 @@ struct Unit {
 };
 // Units are ordered super-block-major: all (corpus tile, query group) units of the first `sb_tiles` query
 // tiles, then the next super-block...  Within a super-block consecutive units share a corpus tile.
+// (32-bit arithmetic: launch_cfg() refuses plans of 2^31 units or more; the 64-bit divisions cost the MMA-issuing
+// warp a few hundred clocks per unit)
 __device__ __forceinline__ Unit decode_unit(const Params& p, int64_t u, int worker) {
   Unit x;
-  const int sb = static_cast<int>(u / p.units_per_sb);
-  const int64_t r = u - static_cast<int64_t>(sb) * p.units_per_sb;
-  x.t = static_cast<int>(r / p.n_mgroups);
-  const int g = static_cast<int>(r - static_cast<int64_t>(x.t) * p.n_mgroups);
+  const uint32_t u32 = static_cast<uint32_t>(u), per_sb = static_cast<uint32_t>(p.units_per_sb);
+  const int sb = static_cast<int>(u32 / per_sb);
+  const uint32_t r = u32 - static_cast<uint32_t>(sb) * per_sb;
+  x.t = static_cast<int>(r / static_cast<uint32_t>(p.n_mgroups));
+  const int g = static_cast<int>(r - static_cast<uint32_t>(x.t) * static_cast<uint32_t>(p.n_mgroups));
   const int sb_end = min(p.m_tiles, (sb + 1) * p.sb_tiles);
   x.mt0 = sb * p.sb_tiles + g * p.m_group;
   x.len = max(0, min(sb_end, x.mt0 + p.m_group) - x.mt0);
@@ -426,21 +429,23 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA only) =================
-    if (lane == 0 && rank == 0) {
+    // The whole warp walks the loop in uniform control flow and one elected lane issues (see umma_bf16_pair_warp).
+    if (rank == 0) {
       constexpr uint32_t idesc = ptx::idesc_bf16_f32(C::TILE_M, BN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       UnitFeed<DYN, PAIR> feed;
       feed.init(worker, n_workers, p.n_units, sched_full, sched_empty, sched_box, rank);
-      while (feed.template next<false>(true)) {
+      const uint64_t desc0 = ptx::smem_desc_k_sw128(ptx::smem_u32(smem));   // stage 0, query operand
+      while (feed.template next<true>(lane == 0)) {
         const int64_t u = feed.u;
         const Unit un = decode_unit(p, u, worker);
         for (int i = 0; i < un.len; ++i) {
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             ptx::mbar_wait(&full_bar[stage], phase);           // TMA bytes (of both CTAs) have landed
             ptx::tc_fence_after_sync();
-            const uint32_t sa = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
-            const uint64_t da = ptx::smem_desc_k_sw128(sa);
+            // (start address field = bytes >> 4; a stage never crosses the field's 256 KB range)
+            const uint64_t da = desc0 + static_cast<uint64_t>((stage * C::STAGE_BYTES) >> 4);
 #pragma unroll
             for (int j = 0; j < NB; ++j) {
               const int slot = NB == 1 ? acc : j;
@@ -449,24 +454,24 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
                 ptx::tc_fence_after_sync();
               }
               const uint32_t tmem_d = tmem_base + slot * BN;
-              const uint64_t db = ptx::smem_desc_k_sw128(sa + A_BYTES + j * C::B_BYTES);
+              const uint64_t db = da + static_cast<uint64_t>((A_BYTES + j * C::B_BYTES) >> 4);
 #pragma unroll
               for (int kk = 0; kk < BK / UMMA_K; ++kk) {
                 // +32 bytes along K inside the 128-byte swizzle row = +2 in the (addr >> 4) field
-                if (PAIR) ptx::umma_bf16_pair(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
-                else ptx::umma_bf16(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
+                if (PAIR) ptx::umma_bf16_pair_warp(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
+                else ptx::umma_bf16_warp(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
               }
             }
             // frees the smem slot (in both CTAs) when the MMAs retire
-            if (PAIR) ptx::umma_commit_pair(&empty_bar[stage], 0x3);
-            else ptx::umma_commit(&empty_bar[stage]);
+            if (PAIR) ptx::umma_commit_pair_warp(&empty_bar[stage], 0x3);
+            else ptx::umma_commit_warp(&empty_bar[stage]);
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
 #pragma unroll
           for (int j = 0; j < NB; ++j) {                        // accumulator(s) complete -> epilogue warps
             const int slot = NB == 1 ? acc : j;
-            if (PAIR) ptx::umma_commit_pair(&tfull_bar[slot], 0x3);
-            else ptx::umma_commit(&tfull_bar[slot]);
+            if (PAIR) ptx::umma_commit_pair_warp(&tfull_bar[slot], 0x3);
+            else ptx::umma_commit_warp(&tfull_bar[slot]);
           }
           if (NB == 2) acc_phase ^= 1;
           else if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
@@ -723,6 +728,7 @@ int launch_cfg(const void* a_op, int64_t nq, int64_t a_ld, const void* b_op, int
   p.nv = nv;
   p.k_blocks = k / BK;
   plan_schedule(p, C::TILE_M, C::TILE_N, k, workers_max);
+  if (p.n_units >= (int64_t(1) << 31)) return fail(XMVE_ERR_LIMIT, "score: more than 2^31 work units");
   const int workers = static_cast<int>(p.n_units < workers_max ? p.n_units : workers_max);
   const int grid = workers * C::CTAS;
   void (*kern)(const CUtensorMap, const CUtensorMap, const Params) =

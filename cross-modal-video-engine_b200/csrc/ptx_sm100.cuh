@@ -282,6 +282,54 @@ __device__ __forceinline__ void umma_bf16_warp(uint32_t tmem_d, uint64_t desc_a,
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One 64-wide k-block = four K = 16 MMAs on consecutive 32-byte slices of the swizzled operand rows (+2 in the
+// descriptors' start-address field), issued in ONE statement: one election, and the descriptors are handed over as
+// their low words only -- the high word (SBO = 1024 B, version 1, SWIZZLE_128B) is the constant DESC_HI -- so that
+// each MMA costs two register-to-uniform moves instead of five.  `first` = 0 overwrites the accumulator in the first
+// MMA (start of a tile).  CTA_GROUP is 1 or 2.
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+template <int CTA_GROUP>
+__device__ __forceinline__ void umma_bf16_kblock_warp(uint32_t tmem_d, uint32_t desc_a_lo, uint32_t desc_b_lo,
+                                                      uint32_t idesc, uint32_t first) {
+  static_assert(CTA_GROUP == 1 || CTA_GROUP == 2, "cta_group is 1 or 2");
+  if (CTA_GROUP == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p, pe;\n\t.reg .b32 a1, a2, a3, b1, b2, b3;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "add.u32 a1, %1, 2;\n\tadd.u32 a2, %1, 4;\n\tadd.u32 a3, %1, 6;\n\t"
+        "add.u32 b1, %2, 2;\n\tadd.u32 b2, %2, 4;\n\tadd.u32 b3, %2, 6;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+        "mov.b64 da, {a1, %5};\n\tmov.b64 db, {b1, %5};\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, 1;\n\t"
+        "mov.b64 da, {a2, %5};\n\tmov.b64 db, {b2, %5};\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, 1;\n\t"
+        "mov.b64 da, {a3, %5};\n\tmov.b64 db, {b3, %5};\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, 1;\n\t}"
+        :
+        : "r"(tmem_d), "r"(desc_a_lo), "r"(desc_b_lo), "r"(idesc), "r"(first), "n"(DESC_HI)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, pe;\n\t.reg .b32 a1, a2, a3, b1, b2, b3;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "add.u32 a1, %1, 2;\n\tadd.u32 a2, %1, 4;\n\tadd.u32 a3, %1, 6;\n\t"
+        "add.u32 b1, %2, 2;\n\tadd.u32 b2, %2, 4;\n\tadd.u32 b3, %2, 6;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "mov.b64 da, {a1, %5};\n\tmov.b64 db, {b1, %5};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n\t"
+        "mov.b64 da, {a2, %5};\n\tmov.b64 db, {b2, %5};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n\t"
+        "mov.b64 da, {a3, %5};\n\tmov.b64 db, {b3, %5};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n\t}"
+        :
+        : "r"(tmem_d), "r"(desc_a_lo), "r"(desc_b_lo), "r"(idesc), "r"(first), "n"(DESC_HI)
+        : "memory");
+  }
+}
 __device__ __forceinline__ void umma_commit_pair_warp(uint64_t* bar, uint16_t mask) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"

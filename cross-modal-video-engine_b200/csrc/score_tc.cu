@@ -436,7 +436,9 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
       uint32_t phase = 0, acc_phase = 0;
       UnitFeed<DYN, PAIR> feed;
       feed.init(worker, n_workers, p.n_units, sched_full, sched_empty, sched_box, rank);
-      const uint64_t desc0 = ptx::smem_desc_k_sw128(ptx::smem_u32(smem));   // stage 0, query operand
+      // low word of the shared-memory descriptors: start address >> 4 | LBO field; stage 0, query operand
+      const uint32_t desc0 = static_cast<uint32_t>(ptx::smem_desc_k_sw128(ptx::smem_u32(smem)));
+      static_assert(BK / UMMA_K == 4, "umma_bf16_kblock_warp issues four K = 16 MMAs");
       while (feed.template next<true>(lane == 0)) {
         const int64_t u = feed.u;
         const Unit un = decode_unit(p, u, worker);
@@ -444,8 +446,8 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             ptx::mbar_wait(&full_bar[stage], phase);           // TMA bytes (of both CTAs) have landed
             ptx::tc_fence_after_sync();
-            // (start address field = bytes >> 4; a stage never crosses the field's 256 KB range)
-            const uint64_t da = desc0 + static_cast<uint64_t>((stage * C::STAGE_BYTES) >> 4);
+            // (start address field = bytes >> 4; the ring stays inside the field's 256 KB range)
+            const uint32_t da = desc0 + static_cast<uint32_t>((stage * C::STAGE_BYTES) >> 4);
 #pragma unroll
             for (int j = 0; j < NB; ++j) {
               const int slot = NB == 1 ? acc : j;
@@ -454,13 +456,8 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
                 ptx::tc_fence_after_sync();
               }
               const uint32_t tmem_d = tmem_base + slot * BN;
-              const uint64_t db = da + static_cast<uint64_t>((A_BYTES + j * C::B_BYTES) >> 4);
-#pragma unroll
-              for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                // +32 bytes along K inside the 128-byte swizzle row = +2 in the (addr >> 4) field
-                if (PAIR) ptx::umma_bf16_pair_warp(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
-                else ptx::umma_bf16_warp(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
-              }
+              const uint32_t db = da + static_cast<uint32_t>((A_BYTES + j * C::B_BYTES) >> 4);
+              ptx::umma_bf16_kblock_warp<C::CTAS>(tmem_d, da, db, idesc, kb != 0 ? 1u : 0u);
             }
             // frees the smem slot (in both CTAs) when the MMAs retire
             if (PAIR) ptx::umma_commit_pair_warp(&empty_bar[stage], 0x3);

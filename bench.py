@@ -32,6 +32,7 @@ The other BASELINE configs are measured by the same run, after the headline, wit
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -80,6 +81,8 @@ def parse():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-verify", action="store_true", help="skip the fp64 check against regenerated rows")
     ap.add_argument("--no-extra-configs", action="store_true", help="C5 only: do not also measure C2-C4")
+    ap.add_argument("--no-head-stream", action="store_true",
+                    help="C5: keep K1 / sampling / threshold of the next batch on the main stream (A/B switch)")
     return ap.parse_args()
 
 
@@ -562,24 +565,48 @@ def bench_c5(ctx, args, steps, warmup):
     torch.cuda.synchronize()
     # the pass over the whole shard (b_row_step == 1), not the sampled one
     filt_events, unhook = ctx.hook(lambda name, a: name == "xmve_score_filter" and a[6] == 1)
+    # K1 / sampling / threshold of batch i+1 go to a second stream: they run next to the rescore / selection / merge of
+    # batch i once FILTER(i) has left the SMs (engine.search_shards, head_stream)
+    head = None if args.no_head_stream else torch.cuda.Stream(device=device)
     step_device, finish_device = pipelined(
-        lambda: distributed.sharded_search(store, q_dev, k, weights=WEIGHTS, n_total=args.nv, defer=True))
+        lambda: distributed.sharded_search(store, q_dev, k, weights=WEIGHTS, n_total=args.nv, defer=True,
+                                           head_stream=head))
     r_lo, r_hi = distributed.shard_range(nq, world, rank)   # result rows this rank hands back to the host
+    host_out = [(out_s_host, out_i_host),
+                (torch.empty_like(out_s_host).pin_memory(), torch.empty_like(out_i_host).pin_memory())]
+    e2e_flight, e2e_count = [], [0]
+
+    def e2e_resolve(item):
+        p, done, (hs, hi_) = item
+        done.synchronize()                                  # ONE host sync per step: results + certificate count
+        s, i = p.result()
+        if p.reran:                                         # rows were re-run: hand the corrected lists back
+            hs[r_lo:r_hi].copy_(s[r_lo:r_hi], non_blocking=True)
+            hi_[r_lo:r_hi].copy_(i[r_lo:r_hi], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return s, i
 
     def step_e2e():
         # host buffers in, host buffers out: the batch crosses PCIe once per node (each rank uploads its slice,
-        # NVLink all-gather), every rank returns its slice of the result rows
-        q = distributed.upload_rows(q_host, device=device)
-        p = distributed.sharded_search(store, q, k, weights=WEIGHTS, n_total=args.nv, defer=True)
-        out_s_host[r_lo:r_hi].copy_(p.scores[r_lo:r_hi], non_blocking=True)
-        out_i_host[r_lo:r_hi].copy_(p.idx[r_lo:r_hi], non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # ONE host sync per step: results + certificate count
-        s, i = p.result()
-        if p.reran:                                         # rows were re-run: hand the corrected lists back
-            out_s_host[r_lo:r_hi].copy_(s[r_lo:r_hi], non_blocking=True)
-            out_i_host[r_lo:r_hi].copy_(i[r_lo:r_hi], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        return s, i
+        # NVLink all-gather), every rank returns its slice of the result rows.  One step stays in flight: the upload
+        # and the head of step i+1 are enqueued before the host waits for the results of step i (two sets of pinned
+        # result buffers alternate).
+        with torch.cuda.stream(head) if head is not None else contextlib.nullcontext():
+            q = distributed.upload_rows(q_host, device=device)
+        p = distributed.sharded_search(store, q, k, weights=WEIGHTS, n_total=args.nv, defer=True, head_stream=head)
+        hs, hi_ = host_out[e2e_count[0] % 2]
+        e2e_count[0] += 1
+        hs[r_lo:r_hi].copy_(p.scores[r_lo:r_hi], non_blocking=True)
+        hi_[r_lo:r_hi].copy_(p.idx[r_lo:r_hi], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        e2e_flight.append((p, done, (hs, hi_)))
+        if len(e2e_flight) > 1:
+            e2e_resolve(e2e_flight.pop(0))
+
+    def finish_e2e():
+        while e2e_flight:
+            e2e_resolve(e2e_flight.pop(0))
 
     for _ in range(warmup):
         step_device()
@@ -593,11 +620,17 @@ def bench_c5(ctx, args, steps, warmup):
     clocks = sampler.stop() if sampler else None
     for _ in range(2):
         step_e2e()
-    ms_e2e = ctx.timed(step_e2e, steps)
+    finish_e2e()
+    ms_e2e = ctx.timed(step_e2e, steps, finish_e2e)
     unhook()
     # self-verification (untimed): the digest of the final lists must agree across N; 128 queries are checked against
-    # an fp64 statement built from rows regenerated from the seed (rank 0; the other ranks wait at the barrier)
-    s_fin, i_fin = step_e2e()
+    # an fp64 statement built from rows regenerated from the seed (rank 0; the other ranks wait at the barrier).  The
+    # lists that are checked are the ones the end-to-end path handed back in its pinned host buffers.
+    step_e2e()
+    finish_e2e()
+    hs, hi_ = host_out[(e2e_count[0] - 1) % 2]
+    s_fin, i_fin = distributed.sharded_search(store, q_dev, k, weights=WEIGHTS, n_total=args.nv)
+    e2e_ok = bool(torch.equal(hs[r_lo:r_hi], s_fin[r_lo:r_hi].cpu()) and torch.equal(hi_[r_lo:r_hi], i_fin[r_lo:r_hi].cpu()))
     digest = result_digest(s_fin, i_fin) if rank == 0 else None
     verified, verify_err = None, None
     if rank == 0 and not args.skip_verify:
@@ -605,7 +638,7 @@ def bench_c5(ctx, args, steps, warmup):
         ref_s, ref_i = fp64_topk_regenerated(torch, c5_chunks(synth, torch, device, 0, args.nv), q_dev[sub], DIMS,
                                              WEIGHTS, k)
         verify_err = float((ref_s - s_fin[sub]).abs().max())
-        verified = bool(torch.equal(ref_i, i_fin[sub])) and verify_err <= 1e-12
+        verified = bool(torch.equal(ref_i, i_fin[sub])) and verify_err <= 1e-12 and e2e_ok
     ctx.barrier()
     # one extra, untimed step with phase marks: where the step goes (reported, not part of any timing above)
     st = {}
@@ -646,7 +679,11 @@ def bench_c5(ctx, args, steps, warmup):
         "clocks": clocks,
         "result_sha256": digest, "verified": verified,
         "verify": {"queries": 128, "against": "fp64 torch statement over corpus rows regenerated from the seed "
-                   "(not the store's buffers); idx identical and |score diff| <= 1e-12", "max_abs_err": verify_err},
+                   "(not the store's buffers); idx identical and |score diff| <= 1e-12", "max_abs_err": verify_err,
+                   "e2e_host_buffers_match": e2e_ok},
+        "pipeline": {"steps_in_flight": 2, "head_stream": head is not None,
+                     "note": "K1 / sampling / threshold of batch i+1 on a second CUDA stream next to the rescore / "
+                             "selection / merge of batch i; a step's certificate and results are read one step late"},
         "stages": {"phases_ms": phases, "candidates_per_query_this_rank": cand_mean, "eps": st.get("eps"),
                    "rescored_per_query_this_rank": st.get("rescored_per_query"), "reruns": st.get("reruns", 0)},
     }

@@ -517,6 +517,35 @@ def test_graph_search_replays_equal_the_eager_search(X):
     assert torch.equal(i3, i_ref3) and torch.equal(s3, s_ref3)
 
 
+def test_head_stream_pipelines_batches_without_changing_results(X):
+    """Steps 1-2 (K1, sampling, threshold) of batch i+1 on a second stream while batch i is still in flight: every
+    batch must come back exactly as from the plain call -- the head's tensors cross streams (allocator hand-over) and
+    several searches are pending at once."""
+    nv, d, nq, k = 150_000, 192, 260, 40
+    V = X.synth.gaussian(81, nv, d)
+    store = X.engine.CorpusStore(nv, (d,)).add(torch.from_numpy(V))
+    batches = [torch.from_numpy(X.synth.gaussian(90 + b, nq, d)).cuda() for b in range(5)]
+    want = [store.search(q, k) for q in batches]
+    head = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for rep in range(3):
+        pend = []
+        got = []
+        for q in batches:
+            pend.append(X.engine.search_shards([store], q, k, defer=True, head_stream=head))
+            if len(pend) > 2:
+                got.append(pend.pop(0).result())
+            junk = torch.empty((nq, d), device="cuda").normal_()      # allocator churn between the calls
+            del junk
+        got += [p.result() for p in pend]
+        for (s0, i0), (s1, i1) in zip(want, got):
+            assert torch.equal(i0, i1) and torch.equal(s0, s1)
+    # a host (pinned) batch goes up on the head stream itself
+    qh = batches[0].cpu().pin_memory()
+    s2, i2 = X.engine.search_shards([store], qh, k, head_stream=head)
+    assert torch.equal(i2, want[0][1]) and torch.equal(s2, want[0][0])
+
+
 @pytest.mark.parametrize("nv,k", [(22_000, 2000), (20_000, 8000)])
 def test_deep_lists_over_two_shards(X, nv, k):
     """k = 2000 over a 22 k-row corpus cut into two shards (the sharded path asked row_topj for more

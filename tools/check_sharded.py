@@ -41,6 +41,17 @@ def main():
                 print("nv=%d nq=%d k=%d exclude=%s: %s" % (nv, nq, k, ex is not None, "identical" if same else "MISMATCH"),
                       flush=True)
         if k == 100:
+            # several batches in flight with the head (K1 / sampling / threshold, one all-gather) on its own stream
+            head = torch.cuda.Stream(device=dev)
+            qs = [synth.device_gaussian(nq, sum(dims), 40 + b, dev) for b in range(4)]
+            refs = [full.search(q, k, weights=w) for q in qs]
+            pend = [distributed.sharded_search(shard, q, k, weights=w, n_total=nv, defer=True, head_stream=head)
+                    for q in qs]
+            same = all(bool(torch.equal(p.result()[1], r[1])) and bool(torch.equal(p.result()[0], r[0]))
+                       for p, r in zip(pend, refs))
+            ok = ok and same
+            if rank == 0:
+                print("head stream, 4 batches in flight nv=%d: %s" % (nv, "identical" if same else "MISMATCH"), flush=True)
             # exact ground-truth ranks without the matrix: owner-shard scores (all-reduce max) + per-shard guard-band
             # counts (all-reduce sum) == the same on one store; R@K / MedR / MeanR / mAP identical
             gts = [[int(x) for x in torch.randint(0, nv, (1 + q % 3,), generator=torch.Generator().manual_seed(q))]

@@ -733,16 +733,16 @@ def bench_c4(ctx, args, steps, warmup):
     # one GPU: the fixed-shape search is captured once into a CUDA graph and replayed (engine.GraphSearch): ~25 launches
     # per step would otherwise cost the host more than they cost the GPU
     gs = engine.GraphSearch(store, nq, k, with_exclude=True) if world == 1 else None
+    head = torch.cuda.Stream(device=device) if gs is None else None       # several ranks: see bench_c5
 
     def search(q):
         if gs is not None:
             return gs(q, exclude=reference, defer=True)
-        return distributed.sharded_search(store, q, k, exclude=reference, n_total=nv, defer=True)
+        return distributed.sharded_search(store, q, k, exclude=reference, n_total=nv, defer=True, head_stream=head)
     step_device, finish_device = pipelined(lambda: search(P))
 
     def step_e2e():
-        q = P_host if gs is not None else P_host.to(device, non_blocking=True)   # the graph copies into its own buffer
-        p = search(q)
+        p = search(P_host)            # the graph copies into its own buffer; the eager path uploads on the head stream
         out_i_host.copy_(p.idx, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         s, i = p.result()
@@ -873,11 +873,12 @@ def bench_c3(ctx, args, steps, warmup):
     filt_events, unhook = ctx.hook(lambda name, a: name == "xmve_score_filter" and a[6] == 1)
 
     gs = engine.GraphSearch(store, nq, k) if world == 1 else None          # CUDA-graph replay on one GPU (see C4)
+    head = torch.cuda.Stream(device=device) if gs is None else None       # several ranks: see bench_c5
 
     def search(q):
         if gs is not None:
             return gs(q, defer=True)
-        return engine.search_shards([store], q, k, comm=comm, n_total=nv, defer=True)
+        return engine.search_shards([store], q, k, comm=comm, n_total=nv, defer=True, head_stream=head)
 
     def enqueue():
         p = search(Q)
@@ -886,8 +887,7 @@ def bench_c3(ctx, args, steps, warmup):
     step_device, finish_device = pipelined(enqueue)
 
     def step_e2e():
-        q = Q_host if gs is not None else Q_host.to(device, non_blocking=True)
-        p = search(q)
+        p = search(Q_host)            # the graph copies into its own buffer; the eager path uploads on the head stream
         ap, _ = avs.ap_at_k(p.idx, sets, nv, k, on_device=True)
         out_i_host.copy_(p.idx, non_blocking=True)
         ap_host.copy_(ap, non_blocking=True)

@@ -4,11 +4,13 @@
 //
 // Persistent, warp-specialised, one CTA per SM:
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B swizzle, multi-stage smem ring)
-//   warp 1      MMA issuer     (tcgen05.mma, fp32 accumulators in TMEM; one elected thread)
+//   warp 1      MMA issuer     (tcgen05.mma, fp32 accumulators in TMEM; the warp walks the loop in uniform control
+//                              flow, elect.sync picks the issuing lane)
 //   warp 2      TMEM allocator (512 columns = two 256-column accumulator slots)
 //   warps 4-11  epilogue       (tcgen05.ld, one query row per thread; two warps share each TMEM lane quarter)
 // Two epilogues share the main loop:
-//   STORE   out = alpha * S                                   (cal_error / sampling pass)
+//   STORE   out = alpha * S                                   (cal_error / sampling pass), written as whole 128-byte
+//           row segments through a swizzled shared-memory tile
 //   FILTER  per-row window (lo, hi]: count scores above hi, append (score, index) of scores inside
 //           the window to a per-row candidate list -- the score matrix never reaches HBM.
 //
@@ -22,7 +24,8 @@
 //   WIDE (2, 6)  a CTA pair computes 256 queries x 512 corpus rows: per k-block each CTA stages its 128 query rows
 //               ONCE plus its halves of TWO corpus sub-tiles and the leader issues two cta_group::2 MMA chains that
 //               share the query operand (48 KB per SM per 1024 tensor clocks -- the fewest operand bytes per flop).
-//               Both accumulator slots belong to one tile, so the epilogue is not overlapped.
+//               Both accumulator slots belong to one tile, so the epilogue is not overlapped (kept for experiments:
+//               launch() no longer chooses it).
 // Unit assignment: static (worker, worker + n_workers, ...) or DYNAMIC -- a scheduler thread (warp 3 of the leader
 // CTA) takes the next unit from a global counter and hands it to the producer, MMA and epilogue roles of both CTAs
 // through a two-slot shared-memory mailbox, so the units of one corpus tile are always in flight together.

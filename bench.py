@@ -872,13 +872,12 @@ def bench_c3(ctx, args, steps, warmup):
     torch.cuda.synchronize()
     filt_events, unhook = ctx.hook(lambda name, a: name == "xmve_score_filter" and a[6] == 1)
 
-    gs = engine.GraphSearch(store, nq, k) if world == 1 else None          # CUDA-graph replay on one GPU (see C4)
-    head = torch.cuda.Stream(device=device) if gs is None else None       # several ranks: see bench_c5
+    # CUDA-graph replay (see C4) -- on several ranks too, with the NCCL gathers captured inside the graph: 60 queries
+    # over 135 k-row shards are bound by the ~40 launches of the eager step (tools/graph_sharded_check.py)
+    gs = engine.GraphSearch(store, nq, k, comm=comm, n_total=nv)
 
     def search(q):
-        if gs is not None:
-            return gs(q, defer=True)
-        return engine.search_shards([store], q, k, comm=comm, n_total=nv, defer=True, head_stream=head)
+        return gs(q, defer=True)
 
     def enqueue():
         p = search(Q)

@@ -737,8 +737,11 @@ class GraphSearch:
         gs = GraphSearch(store, n_queries=60, k=1000)
         scores, idx = gs(queries)                 # or  p = gs(queries, defer=True); ...; p.result()
 
-    One shard per process without a process group (``comm``) is the tested configuration; the returned tensors are
-    the graph's static output buffers and are overwritten by the next call.
+    With ``comm`` (``distributed.GroupComm``) the NCCL gathers of a sharded search are captured inside the graph and
+    every rank replays in lockstep (``tools/check_sharded.py`` / ``tools/graph_sharded_check.py``: identical to the
+    eager search; 0.94 -> 0.64 ms for 60 queries over two 135 k-row shards, where the ~40 launches of the eager step
+    are what bounds it).  The returned tensors are the graph's static output buffers and are overwritten by the
+    next call.
     """
 
     def __init__(self, stores, n_queries, k, weights=None, with_exclude=False, comm=None, n_total=None,

@@ -66,6 +66,18 @@ def main():
                 print("rank_of_gt nv=%d: %s (median rank %.1f)" % (nv, "identical" if same else "MISMATCH",
                                                                    b.recall_medr_meanr()[3]), flush=True)
         if k == 1000:
+            # the same search captured once into a CUDA graph WITH its NCCL gathers and replayed on every rank
+            gs = engine.GraphSearch(shard, nq, k, weights=w, comm=distributed.GroupComm(), n_total=nv)
+            same = True
+            for b in range(3):
+                qb = synth.device_gaussian(nq, sum(dims), 60 + b, dev)
+                s_ref, i_ref = full.search(qb, k, weights=w)
+                s_g, i_g = gs(qb)
+                same = same and bool(torch.equal(i_g, i_ref)) and bool(torch.equal(s_g, s_ref))
+            ok = ok and same
+            del gs
+            if rank == 0:
+                print("CUDA-graph replay over NCCL nv=%d k=%d: %s" % (nv, k, "identical" if same else "MISMATCH"), flush=True)
             rel = [sorted(set(np.random.default_rng(q).integers(0, nv, 300).tolist())) for q in range(nq)]
             s, i = avs.search_avs(shard, Q, k, weights=w, comm=distributed.GroupComm(), n_total=nv)
             ap, m = avs.ap_at_k(i, rel, nv, k)

@@ -64,54 +64,97 @@ gt_ranks_rows_kernel(const T* __restrict__ x, int64_t n_query, int64_t n_col, in
   }
 }
 
-// axis 1: query = column i, memories = rows.  A block owns 32 adjacent columns (lane <-> column, so
-// every row read is one coalesced line) and a slice of the rows; partial counts are added atomically
-// into ranks[] (zeroed by the host wrapper; slice 0 adds the leading 1).  G ground-truth entries are ranked per
-// pass over the data: G = 24 covers the 20 captions per video of MSR-VTT in ONE pass.
-template <typename T, int G>
+// axis 1: query = column i, memories = rows.  A block owns 32 adjacent columns (lane <-> column, so every row read
+// is one coalesced line) and a slice of the rows; partial counts are added atomically into ranks[] (zeroed by the
+// host wrapper; slice 0 adds the leading 1).  Up to CG ground-truth entries per column are ranked in one pass over
+// the data (the 20 captions per video of MSR-VTT).
+//
+// rank(g) - 1 = #{m : (x[m], m) < (x[g], g)} lexicographically.  The column's ground-truth keys are sorted once
+// (shared memory, one lane per column); an element then needs ONE branch-free binary search (five steps) for
+// p = #{g : key_g <= (x[m], m)} and one private histogram bump -- the count of entry g is the prefix sum of the
+// histogram up to g.  The first version compared every element with all 24 entries (~100 instructions and 96 live
+// registers per element: 16 warps per SM, 0.37 TB/s over the 1.43 GB matrix of the C2 shape).
+constexpr int CG = 31;                                   // entries per pass (the sorted list is padded to 32)
+template <typename T>
 __global__ void __launch_bounds__(256)
 gt_ranks_cols_kernel(const T* __restrict__ x, int64_t n_row, int64_t n_col, int64_t ld,
                      const int64_t* __restrict__ gt_off, const int32_t* __restrict__ gt_ids, int max_gt,
                      int rows_per_slice, int32_t* __restrict__ ranks) {
+  __shared__ T s_key[32][32];                            // [sorted position][column of the block]
+  __shared__ int s_row[32][32];                          // ... its row (the tie rule) ...
+  __shared__ int s_ent[32][32];                          // ... and its place in the column's CSR list
+  __shared__ int s_hist[32][256];                        // [p][thread]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t col = static_cast<int64_t>(blockIdx.x) * 32 + lane;
   const bool col_ok = col < n_col;
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_slice;
   const int64_t r1 = min(n_row, r0 + rows_per_slice);
   const int64_t e_lo = col_ok ? gt_off[col] : 0, e_hi = col_ok ? gt_off[col + 1] : 0;
-  for (int base = 0; base < max_gt; base += G) {
-    T gv[G];
-    int gi[G], cnt[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const bool ok = e_lo + base + g < e_hi;
-      gi[g] = ok ? gt_ids[e_lo + base + g] : -1;
-      gv[g] = ok ? x[static_cast<int64_t>(gi[g]) * ld + col] : static_cast<T>(0);
-      cnt[g] = 0;
-    }
-    if (col_ok) {
-      int64_t m = r0 + warp;
-      for (; m + 8 < r1; m += 16) {                              // two independent row reads in flight
-        const T va = x[m * ld + col], vb = x[(m + 8) * ld + col];
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          cnt[g] += (va < gv[g] || (va == gv[g] && m < gi[g])) ? 1 : 0;
-          cnt[g] += (vb < gv[g] || (vb == gv[g] && m + 8 < gi[g])) ? 1 : 0;
+  const T inf = static_cast<T>(CUDART_INF);
+  for (int base = 0; base < max_gt; base += CG) {
+    if (warp == 0) {                                     // one lane per column: gather and insertion-sort its keys
+      int ng = 0;
+      for (int g = 0; g < CG; ++g) {
+        if (e_lo + base + g >= e_hi) break;
+        const int gi = gt_ids[e_lo + base + g];
+        T gv = x[static_cast<int64_t>(gi) * ld + col];
+        int gr = gi;
+        if (gv != gv) { gv = -inf; gr = -1; }           // NaN ground truth: nothing compares below it (rank 1)
+        int pos = ng;
+        while (pos > 0 && (s_key[pos - 1][lane] > gv || (s_key[pos - 1][lane] == gv && s_row[pos - 1][lane] > gr))) {
+          s_key[pos][lane] = s_key[pos - 1][lane];
+          s_row[pos][lane] = s_row[pos - 1][lane];
+          s_ent[pos][lane] = s_ent[pos - 1][lane];
+          --pos;
         }
+        s_key[pos][lane] = gv;
+        s_row[pos][lane] = gr;
+        s_ent[pos][lane] = base + g;
+        ++ng;
       }
-      for (; m < r1; m += 8) {
-        const T v = x[m * ld + col];
-#pragma unroll
-        for (int g = 0; g < G; ++g) cnt[g] += (v < gv[g] || (v == gv[g] && m < gi[g])) ? 1 : 0;
-      }
-    }
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      if (gi[g] >= 0) {
-        const int add = cnt[g] + ((blockIdx.y == 0 && warp == 0) ? 1 : 0);
-        if (add != 0) atomicAdd(&ranks[e_lo + base + g], add);
+      for (int g = ng; g < 32; ++g) {                    // padding: above every element
+        s_key[g][lane] = inf;
+        s_row[g][lane] = 0x7fffffff;
+        s_ent[g][lane] = -1;
       }
     }
+#pragma unroll
+    for (int p = 0; p < 32; ++p) s_hist[p][threadIdx.x] = 0;
+    __syncthreads();
+    if (col_ok) {
+      auto bump = [&](T v, int64_t m) {
+        if (v != v) return;                              // NaN elements are below nothing
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const T k = s_key[lo + step - 1][lane];
+          const bool le = k < v || (k == v && static_cast<int64_t>(s_row[lo + step - 1][lane]) <= m);
+          lo += le ? step : 0;
+        }
+        ++s_hist[lo][threadIdx.x];                       // lo = #{g : key_g <= (v, m)}  (<= 31)
+      };
+      int64_t m = r0 + warp;
+      for (; m + 24 < r1; m += 32) {                     // four independent row reads in flight
+        const T va = x[m * ld + col], vb = x[(m + 8) * ld + col], vc = x[(m + 16) * ld + col],
+                vd = x[(m + 24) * ld + col];
+        bump(va, m);
+        bump(vb, m + 8);
+        bump(vc, m + 16);
+        bump(vd, m + 24);
+      }
+      for (; m < r1; m += 8) bump(x[m * ld + col], m);
+    }
+    // entry at sorted position g is preceded by every element whose p is <= g
+    int run = 0;
+    for (int g = 0; g < 32; ++g) {
+      run += s_hist[g][threadIdx.x];
+      const int ent = s_ent[g][lane];
+      if (ent >= 0) {
+        const int add = run + ((blockIdx.y == 0 && warp == 0) ? 1 : 0);
+        if (add != 0) atomicAdd(&ranks[e_lo + ent], add);
+      }
+    }
+    __syncthreads();                                     // the sorted lists are rebuilt by the next pass
   }
 }
 
@@ -271,12 +314,12 @@ extern "C" int xmve_gt_ranks(const void* errors, int dtype, int64_t n_row, int64
     rows_per_slice = (rows_per_slice + 15) / 16 * 16;
     slices = static_cast<int>((n_row + rows_per_slice - 1) / rows_per_slice);
     dim3 grid(static_cast<unsigned>(col_blocks), static_cast<unsigned>(slices));
-#define XMVE_COLS(T, GG)                                                                                          \
-  gt_ranks_cols_kernel<T, GG><<<grid, 256, 0, st>>>(static_cast<const T*>(errors), n_row, n_col, ld, gt_off, gt_ids,   \
-                                                    max_gt, rows_per_slice, ranks)
-    if (dtype == XMVE_F32) { if (max_gt <= 8) XMVE_COLS(float, 8); else XMVE_COLS(float, 24); }
-    else { if (max_gt <= 8) XMVE_COLS(double, 8); else XMVE_COLS(double, 24); }
-#undef XMVE_COLS
+    if (dtype == XMVE_F32)
+      gt_ranks_cols_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(errors), n_row, n_col, ld, gt_off,
+                                                        gt_ids, max_gt, rows_per_slice, ranks);
+    else
+      gt_ranks_cols_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(errors), n_row, n_col, ld, gt_off,
+                                                         gt_ids, max_gt, rows_per_slice, ranks);
   }
   return launch_status("gt_ranks kernel");
 }

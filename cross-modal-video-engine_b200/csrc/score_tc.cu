@@ -150,7 +150,7 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 // scan, but its result is first needed when the parked pairs are stored -- after the NEXT tile's scan (the
 // lists are double-buffered).  With the stores directly behind the atomic every epilogue warp sat out one L2
 // atomic round trip (~1.5 us) per tile, because almost every warp has some lane with a candidate: 3.5-4 us of
-// epilogue against 4.4 us of MMA per tile at K = 640 (profiles/r2_summary.md section 2).
+// epilogue against 4.4 us of MMA per tile at K = 640 (profiles/r2_summary.md section 6).
 constexpr int STG = 8;                                   // parked candidates per thread and list
 __device__ __forceinline__ void store_parked(float* cand_score, int32_t* cand_idx, int cap, int64_t row, int base,
                                              const uint2* stg, int n) {

@@ -586,9 +586,14 @@ def bench_c5(ctx, args, steps, warmup):
             torch.cuda.current_stream().synchronize()
         return s, i
 
-    e2e_new = []
-
-    def e2e_copy_out(p):
+    def step_e2e():
+        # host buffers in, host buffers out: the batch crosses PCIe once per node (each rank uploads its slice,
+        # NVLink all-gather), every rank returns its slice of the result rows.  One step stays in flight: the upload
+        # and the head of step i+1 are enqueued before the host waits for the results of step i (two sets of pinned
+        # result buffers alternate).
+        with torch.cuda.stream(head) if head is not None else contextlib.nullcontext():
+            q = distributed.upload_rows(q_host, device=device)
+        p = distributed.sharded_search(store, q, k, weights=WEIGHTS, n_total=args.nv, defer=True, head_stream=head)
         hs, hi_ = host_out[e2e_count[0] % 2]
         e2e_count[0] += 1
         hs[r_lo:r_hi].copy_(p.scores[r_lo:r_hi], non_blocking=True)
@@ -596,25 +601,10 @@ def bench_c5(ctx, args, steps, warmup):
         done = torch.cuda.Event()
         done.record()
         e2e_flight.append((p, done, (hs, hi_)))
-
-    def step_e2e():
-        # host buffers in, host buffers out: the batch crosses PCIe once per node (each rank uploads its slice,
-        # NVLink all-gather), every rank returns its slice of the result rows.  The pipeline stays full: the upload and
-        # the head of step i+1 are enqueued (which also enqueues the tail of step i, engine.search_shards) before the
-        # results of step i are copied out, and the host waits for a step's results one step later still (two sets of
-        # pinned result buffers alternate).
-        with torch.cuda.stream(head) if head is not None else contextlib.nullcontext():
-            q = distributed.upload_rows(q_host, device=device)
-        e2e_new.append(distributed.sharded_search(store, q, k, weights=WEIGHTS, n_total=args.nv, defer=True,
-                                                  head_stream=head))
-        if len(e2e_new) > 1:
-            e2e_copy_out(e2e_new.pop(0))
         if len(e2e_flight) > 1:
             e2e_resolve(e2e_flight.pop(0))
 
     def finish_e2e():
-        while e2e_new:
-            e2e_copy_out(e2e_new.pop(0).flush())
         while e2e_flight:
             e2e_resolve(e2e_flight.pop(0))
 
@@ -692,9 +682,8 @@ def bench_c5(ctx, args, steps, warmup):
                    "(not the store's buffers); idx identical and |score diff| <= 1e-12", "max_abs_err": verify_err,
                    "e2e_host_buffers_match": e2e_ok},
         "pipeline": {"steps_in_flight": 2, "head_stream": head is not None,
-                     "note": "K1 / sampling / threshold of batch i+1 on a second CUDA stream, enqueued BEFORE the "
-                             "rescore / selection / merge of batch i, so that the two run side by side after "
-                             "FILTER(i); a step's certificate and results are read one step late (end to end: two)"},
+                     "note": "K1 / sampling / threshold of batch i+1 on a second CUDA stream next to the rescore / "
+                             "selection / merge of batch i; a step's certificate and results are read one step late"},
         "stages": {"phases_ms": phases, "candidates_per_query_this_rank": cand_mean, "eps": st.get("eps"),
                    "rescored_per_query_this_rank": st.get("rescored_per_query"), "reruns": st.get("reruns", 0)},
     }
@@ -753,9 +742,7 @@ def bench_c4(ctx, args, steps, warmup):
     step_device, finish_device = pipelined(lambda: search(P))
 
     def step_e2e():
-        # the graph copies into its own buffer; the eager path uploads on the head stream, and its rescore / selection /
-        # merge are enqueued by flush() (they would otherwise wait for the next search call)
-        p = search(P_host).flush()
+        p = search(P_host)            # the graph copies into its own buffer; the eager path uploads on the head stream
         out_i_host.copy_(p.idx, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         s, i = p.result()

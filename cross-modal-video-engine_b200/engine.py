@@ -522,18 +522,6 @@ class PendingSearch:
         p.scores, p.idx = scores, idx
         return p
 
-    def flush(self):
-        """With ``head_stream`` the rescore / selection / merge of a batch are enqueued by the NEXT search call;
-        ``flush`` enqueues them now (e.g. before copying ``scores`` / ``idx`` to the host without waiting).  Returns
-        ``self``."""
-        if not self._done and self._ctx is not None and self._ctx.tail_pending():
-            if self._ctx.dev.type == "cuda":
-                with torch.cuda.device(self._ctx.dev):
-                    _flush_tail(self._ctx)
-            else:
-                _flush_tail(self._ctx)
-        return self
-
     def result(self):
         if not self._done:
             if self._ctx.dev.type == "cuda":
@@ -569,11 +557,7 @@ class _Search:
 
     # one pass over all rows (rows None) or over the rows that are re-run --------------------------------
     def run_pass(self, rows):
-        return self._tail_stage(self._filter_stage(rows), rows)
-
-    def _filter_stage(self, rows):
-        """Step 3 (the FILTER launches) -> what the tail needs."""
-        ref, dev, ph = self.ref, self.dev, self.ph
+        ref, dev, comm, ph, k_eff, kk, eps_t = self.ref, self.dev, self.comm, self.ph, self.k_eff, self.kk, self.eps_t
         if rows is None:
             a_sub, q_sub, qn_sub, thr_sub, ex_sub, n_sub = self.a_op, self.q_raw, self.q_norm, self.thr, self.excl, self.nq
         else:
@@ -589,12 +573,6 @@ class _Search:
         ph.mark("alloc")
         cands = [s._filter(a_sub, n_sub, thr_sub, cap) for s in self.live]
         ph.mark("filter")
-        return q_sub, qn_sub, thr_sub, ex_sub, n_sub, cap, cands
-
-    def _tail_stage(self, stage, rows):
-        """Steps 4-5: two-round rescore, selection, merge, certificate."""
-        dev, comm, ph, k_eff, kk, eps_t = self.dev, self.comm, self.ph, self.k_eff, self.kk, self.eps_t
-        q_sub, qn_sub, thr_sub, ex_sub, n_sub, cap, cands = stage
         # 4: what needs an exact score
         m = kk if self.solo else min(kk, int(math.ceil(1.5 * kk / self.n_shards)) + 10)
         if kk <= PILOT_MAX and (self.solo or self.n_shards * m <= PILOT_UNION_MAX):
@@ -667,28 +645,8 @@ class _Search:
         return s_, i_, cert, thr_next, over, n_bad, thr_sub
 
     def first_pass(self, in_graph=False, flag_host=None):
-        self.first_filter()
-        self.first_tail(in_graph, flag_host)
-
-    def first_filter(self):
         self._cap0 = self.cap
-        self._stage = self._filter_stage(None)
-        self._main = torch.cuda.current_stream() if self.dev.type == "cuda" else None
-
-    def tail_pending(self):
-        return getattr(self, "_stage", None) is not None
-
-    def first_tail(self, in_graph=False, flag_host=None):
-        """Enqueue steps 4-5 of the first pass behind its FILTER (on the stream the FILTER was launched on)."""
-        if self._main is not None and not in_graph:
-            with torch.cuda.stream(self._main):
-                self._first_tail(in_graph, flag_host)
-        else:
-            self._first_tail(in_graph, flag_host)
-
-    def _first_tail(self, in_graph, flag_host):
-        stage, self._stage = self._stage, None
-        s_, i_, cert, thr_next, over, n_bad, thr_sub = self._tail_stage(stage, None)
+        s_, i_, cert, thr_next, over, n_bad, thr_sub = self.run_pass(None)
         self.out_s[:, :self.k_eff] = s_
         self.out_i[:, :self.k_eff] = i_
         self._last = (cert, thr_next, over, thr_sub)
@@ -713,8 +671,6 @@ class _Search:
 
     def resolve(self):
         """Wait for the first pass's certificate count; re-run (all ranks alike) the rows that missed it."""
-        if self.tail_pending():
-            _flush_tail(self)
         if self._event is not None:
             self._event.synchronize()
         self.ph.mark("certify_sync")
@@ -893,18 +849,6 @@ def search_shards(stores, queries, k, weights=None, exclude=None, eps=None, smal
     return pending if defer else pending.result()
 
 
-#: searches whose FILTER has been enqueued but whose tail has not, by head stream (see _search_shards)
-_TAILS = {}
-
-
-def _flush_tail(search):
-    """Enqueue the tail of ``search`` now (its results were asked for before the next batch arrived)."""
-    for key, val in list(_TAILS.items()):
-        if val is search:
-            del _TAILS[key]
-    search.first_tail()
-
-
 def _head_on(stream):
     import contextlib
     return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
@@ -962,18 +906,7 @@ def _search_shards(stores, queries, k, weights, exclude, eps, small_nv, stats, c
     pl = plan(kk, n_total)
     with _head_on(head_stream):
         eps_t, thr = _threshold(stores, comm, solo, wts, eps, pl, a_op, q_res, nq, ph)
-    search = _Search(stores, comm, k, k_eff, kk, wts, excl, eps_t, pl, a_op, q_raw, q_norm, nq, thr, out_s, out_i,
-                     stats, ph)
-    if head_stream is None:
-        search.first_pass(in_graph, flag_host)
-    else:
-        # Host order decides the order of the collectives on the group's one NCCL stream.  The head of THIS batch
-        # (with its gather) has just been enqueued; only now follow the tail of the PREVIOUS batch (two gathers) and
-        # then this batch's FILTER: head(i+1) and tail(i) run side by side after FILTER(i), and the head's gather does
-        # not queue behind the tail's.  The tail of this batch is enqueued by the next call (or by .result()).
-        prev = _TAILS.pop(id(head_stream), None)
-        if prev is not None and prev.tail_pending():
-            prev.first_tail()
+    if head_stream is not None:
         # step 3 onwards runs on the caller's stream: it waits for the head, and the caching allocator must not hand
         # the head's tensors back to the head stream while this stream still reads them
         main = torch.cuda.current_stream()
@@ -981,8 +914,9 @@ def _search_shards(stores, queries, k, weights, exclude, eps, small_nv, stats, c
         for t in (a_op, q_raw, q_norm, q_res, eps_t, thr, excl):
             if t is not None:
                 t.record_stream(main)
-        search.first_filter()
-        _TAILS[id(head_stream)] = search
+    search = _Search(stores, comm, k, k_eff, kk, wts, excl, eps_t, pl, a_op, q_raw, q_norm, nq, thr, out_s, out_i,
+                     stats, ph)
+    search.first_pass(in_graph, flag_host)
     pending = PendingSearch(search)
     pending._ctx_template = search
     pending.scores, pending.idx = out_s, out_i

@@ -270,8 +270,12 @@ __device__ __forceinline__ void store_chunk(const Params& p, const uint32_t (&v)
 
 // COLS columns of one 128-row accumulator slot -> STORE or FILTER (this thread owns query row st.row).  The TMEM
 // loads are software-pipelined: chunk c+1 is in flight while chunk c is examined.
-template <int MODE, int COLS>
-__device__ __forceinline__ void epilogue_slot(const Params& p, uint32_t taddr, RowState& st, int64_t col0) {
+// `release()` hands the slot back to the MMA warp.  It is called as soon as the LAST chunk has arrived in registers,
+// before that chunk is examined: the accumulator is free from then on, and at K = 640 the MMA warp was waiting for
+// this hand-back (profiles/r2b_mma_issue_loop.txt: ~2 try_wait rounds per tile on `tempty`).
+template <int MODE, int COLS, typename Release>
+__device__ __forceinline__ void epilogue_slot(const Params& p, uint32_t taddr, RowState& st, int64_t col0,
+                                              Release release) {
   const int lane = threadIdx.x & 31;
   uint32_t v0[32], v1[32];
   ptx::tmem_ld_32x32(taddr, v0);
@@ -283,6 +287,7 @@ __device__ __forceinline__ void epilogue_slot(const Params& p, uint32_t taddr, R
     else filter_chunk(p, v0, st, col0 + c * 32);
     ptx::tmem_ld_wait();
     if (c + 2 < COLS / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, v0);
+    else release();
     if (MODE == MODE_STORE) store_chunk(p, v1, st.row - lane, col0 + (c + 1) * 32, reinterpret_cast<float4*>(st.stg - lane * 2 * STG), lane);
     else filter_chunk(p, v1, st, col0 + (c + 1) * 32);
   }
@@ -532,13 +537,14 @@ __device__ __forceinline__ void score_body(const CUtensorMap& tm_a, const CUtens
         }
         ptx::mbar_wait(&tfull_bar[slot], acc_phase);
         ptx::tc_fence_after_sync();
-        epilogue_slot<MODE, C::EPI_COLS>(p, tmem_base + lane_addr + slot * BN + col_in_slot, st, col0);
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) {                                       // one arrival per warp on the LEADER's barrier
-          if (PAIR && rank != 0) ptx::mbar_arrive_remote(&tempty_bar[slot], 0);
-          else ptx::mbar_arrive(&tempty_bar[slot]);
-        }
+        epilogue_slot<MODE, C::EPI_COLS>(p, tmem_base + lane_addr + slot * BN + col_in_slot, st, col0, [&]() {
+          ptx::tc_fence_before_sync();
+          __syncwarp();                                        // every lane's last TMEM load has completed
+          if (lane == 0) {                                     // one arrival per warp on the LEADER's barrier
+            if (PAIR && rank != 0) ptx::mbar_arrive_remote(&tempty_bar[slot], 0);
+            else ptx::mbar_arrive(&tempty_bar[slot]);
+          }
+        });
         if (NB == 2) acc_phase ^= 1;
         else if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
         if (MODE == MODE_FILTER) {                             // the slot is already back with the MMA warp

@@ -1087,6 +1087,9 @@ def bench_c2(ctx, args, steps, warmup):
 BENCHES = {"c5": bench_c5, "c4": bench_c4, "c3": bench_c3, "c2": bench_c2}
 
 
+EXTRA_CONFIGS_LIMIT_S = 420
+
+
 def run_b200_arm(args):
     ctx = Ctx()
     warmup = max(args.warmup, 3)
@@ -1099,6 +1102,23 @@ def run_b200_arm(args):
     if args.config == "c5" and not args.no_extra_configs:
         # the other BASELINE configs, measured by the same run with fewer steps (C2: one GPU only -- replicas)
         extra = {}
+        # An extra config must never cost the headline line -- not even by hanging (a collective that never returns):
+        # after EXTRA_CONFIGS_LIMIT_S every rank prints what it has (rank 0: the headline with the configs measured so
+        # far) and leaves.  Normally the three configs take well under a minute.
+        printed = threading.Lock()
+
+        def give_up():
+            if not printed.acquire(blocking=False):
+                return
+            if ctx.rank == 0:
+                extra.setdefault("error", "extra configs exceeded %d s; the headline line above them stands" %
+                                 EXTRA_CONFIGS_LIMIT_S)
+                line["configs"] = extra
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        watchdog = threading.Timer(EXTRA_CONFIGS_LIMIT_S, give_up)
+        watchdog.daemon = True
+        watchdog.start()
         for name in ("c4", "c3", "c2"):
             if name == "c2" and ctx.world > 1:
                 continue
@@ -1117,6 +1137,9 @@ def run_b200_arm(args):
                     sub["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": host_threads(), "kind": "port",
                                            "sample": sample}
                 extra[name] = sub
+        watchdog.cancel()
+        if not printed.acquire(blocking=False):       # the watchdog is printing: let it finish (it exits the process)
+            time.sleep(60)
         if ctx.rank == 0:
             line["configs"] = extra
     if ctx.rank == 0:

@@ -886,7 +886,7 @@ def bench_c3(ctx, args, steps, warmup):
     step_device, finish_device = pipelined(enqueue)
 
     def step_e2e():
-        p = search(Q_host)            # the graph copies into its own buffer; the eager path uploads on the head stream
+        p = search(Q_host)            # the graph copies the pinned host batch into its own buffer
         ap, _ = avs.ap_at_k(p.idx, sets, nv, k, on_device=True)
         out_i_host.copy_(p.idx, non_blocking=True)
         ap_host.copy_(ap, non_blocking=True)
